@@ -1,0 +1,540 @@
+// univl_b200 — multi-head attention core for short sequences (S <= 256), forward and backward.
+//
+// Reference semantics (modules/module_bert.py:176-196, module_decoder.py:225-245):
+//   scores = Q K^T / sqrt(d)  THEN  + additive mask (-10000 for masked keys — NOT -inf: a fully masked row keeps the
+//   softmax of its raw scores);  P = softmax(scores);  P = dropout(P);  ctx = P V;  heads merged back to [T, H].
+// The decoder's self-attention mask is (key padded OR key index > query index) -> -10000 ONCE (module_decoder.py:395).
+//
+// d = 64, whole K/V of one (sequence, head) live in shared memory, so softmax is exact two-pass (max+sum, then
+// normalised P) and nothing of the [B, h, S, S] score tensor ever reaches HBM.  Tensor work uses warp-level
+// mma.sync m16n8k16 bf16 (the S x S x 64 products are ~4 % of a layer's FLOPs; the projections around them run on
+// tcgen05 — see gemm_tcgen05.cu).  One CTA per (sequence, head); each warp owns 16 query rows (or 16 key rows in the
+// dK/dV pass of backward) at a time.  Backward recomputes P from Q, K and the saved log-sum-exp, flash-style, with
+// no atomics: dQ is produced by query-row tasks, dK/dV by key-row tasks that recompute the transposed tiles.
+// Dropout masks are Philox(seed, stream, element) and regenerated identically in every pass.
+#include "common.cuh"
+
+namespace univl {
+
+constexpr int HD = 64;        // head dim
+constexpr int LDS = 72;       // smem row stride in elements (144 B: conflict-free ldmatrix)
+constexpr int ATT_FWD_WARPS = 4;
+constexpr int ATT_BWD_WARPS = 8;
+
+struct AttnParams {
+  const bf16 *q, *k, *v;
+  long long ldq, ldk, ldv;
+  bf16* o;
+  long long ldo;
+  float* lse;  // [n_seq, heads, Sq]
+  const long long* mask_a;  // [Na, Wa]
+  const long long* mask_b;  // [Nb, Fb] or null
+  int Wa, Fb, Nb, all_pairs;
+  int n_seq, heads, Sq, Sk, causal;
+  float scale;
+  uint32_t drop_threshold;
+  float drop_scale;
+  int drop_on;
+  uint64_t seed, stream;
+  // backward only
+  const bf16* d_o;
+  long long lddo;
+  bf16 *dq, *dk, *dv;
+  long long lddq, lddk, lddv;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// copy `rows` x 64 bf16 (head slice) into smem [rows16][LDS], zero-filling rows >= rows
+__device__ __forceinline__ void load_head_tile(bf16* dst, const bf16* src, long long ld, int rows, int rows16) {
+  for (int idx = threadIdx.x; idx < rows16 * 8; idx += blockDim.x) {
+    const int r = idx >> 3, c = idx & 7;
+    bf16* d = dst + r * LDS + c * 8;
+    if (r < rows) cp_async16(d, src + (long long)r * ld + c * 8);
+    else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// additive key mask for this sequence into smem: 0 / -10000 for real keys, -inf for padding beyond Sk
+__device__ __forceinline__ void build_key_mask(float* madd, const AttnParams& p, int seq, int Sk16) {
+  const long long i = p.all_pairs ? seq / p.Nb : seq;
+  const long long j = p.all_pairs ? seq % p.Nb : seq;
+  for (int c = threadIdx.x; c < Sk16; c += blockDim.x) {
+    float m;
+    if (c >= p.Sk) m = -INFINITY;
+    else {
+      long long v = 1;
+      if (p.mask_a != nullptr) {
+        if (c < p.Wa) v = p.mask_a[i * p.Wa + c];
+        else if (p.mask_b != nullptr) v = p.mask_b[j * p.Fb + (c - p.Wa)];
+      }
+      m = v != 0 ? 0.f : -10000.f;
+    }
+    madd[c] = m;
+  }
+}
+
+// A-operand fragments (16 rows x 64 dims) of smem matrix X starting at row r0
+__device__ __forceinline__ void load_a_frags(const bf16* X, int r0, int lane, uint32_t (&a)[4][4]) {
+  const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) ldsm_x4(smem_u32(X + row * LDS + kc * 16 + (lane >> 4) * 8), a[kc]);
+}
+
+// C[16 x 16] = A(16 x 64) * Y^T where Y rows n0..n0+15 are the "n" index (keys or queries), contraction over dims
+__device__ __forceinline__ void mma_a_yT(const uint32_t (&a)[4][4], const bf16* Y, int n0, int lane, float (&c)[2][4]) {
+#pragma unroll
+  for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[nb][e] = 0.f;
+  const int row = n0 + (lane & 7) + (lane >> 4) * 8;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint32_t b[4];
+    ldsm_x4(smem_u32(Y + row * LDS + kc * 16 + ((lane >> 3) & 1) * 8), b);
+    mma16816(c[0], a[kc], b[0], b[1]);
+    mma16816(c[1], a[kc], b[2], b[3]);
+  }
+}
+
+// acc[16 x 64] += P(16 x 16, bf16 A-fragments) * Z where Z rows k0..k0+15 are the contraction index
+__device__ __forceinline__ void mma_p_z(const uint32_t (&pa)[4], const bf16* Z, int k0, int lane, float (&acc)[8][4]) {
+  const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int nd = 0; nd < 4; ++nd) {
+    uint32_t b[4];
+    ldsm_x4_t(smem_u32(Z + row * LDS + nd * 16 + (lane >> 4) * 8), b);
+    mma16816(acc[2 * nd], pa, b[0], b[1]);
+    mma16816(acc[2 * nd + 1], pa, b[2], b[3]);
+  }
+}
+
+// keep flags for (query i, keys j0, j0+1), j0 even: one Philox call
+__device__ __forceinline__ void keep_pair(const AttnParams& p, long long bh, int i, int j0, int Skq, bool& k0, bool& k1) {
+  const uint4 r = philox4x32(p.seed, p.stream, (uint64_t)((bh * p.Sq + i) * (long long)Skq + (j0 >> 2)));
+  if (j0 & 2) { k0 = r.z < p.drop_threshold; k1 = r.w < p.drop_threshold; }
+  else        { k0 = r.x < p.drop_threshold; k1 = r.y < p.drop_threshold; }
+}
+__device__ __forceinline__ bool keep_one(const AttnParams& p, long long bh, int i, int j, int Skq) {
+  const uint4 r = philox4x32(p.seed, p.stream, (uint64_t)((bh * p.Sq + i) * (long long)Skq + (j >> 2)));
+  const uint32_t w = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
+  return w < p.drop_threshold;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_FWD_WARPS * 32)
+attention_fwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int Sq16 = (p.Sq + 15) & ~15, Sk16 = (p.Sk + 15) & ~15;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
+  bf16* sK = sQ + Sq16 * LDS;
+  bf16* sV = sK + Sk16 * LDS;
+  float* madd = reinterpret_cast<float*>(sV + Sk16 * LDS);
+
+  const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const long long bh = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Skq = Sk16 >> 2;
+
+  load_head_tile(sQ, p.q + (long long)seq * p.Sq * p.ldq + h * HD, p.ldq, p.Sq, Sq16);
+  load_head_tile(sK, p.k + (long long)seq * p.Sk * p.ldk + h * HD, p.ldk, p.Sk, Sk16);
+  load_head_tile(sV, p.v + (long long)seq * p.Sk * p.ldv + h * HD, p.ldv, p.Sk, Sk16);
+  build_key_mask(madd, p, seq, Sk16);
+  cp_async_wait_all();
+  __syncthreads();
+
+  for (int q0 = warp * 16; q0 < Sq16; q0 += ATT_FWD_WARPS * 16) {
+    uint32_t qa[4][4];
+    load_a_frags(sQ, q0, lane, qa);
+    const int i0 = q0 + g, i1 = q0 + g + 8;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    // pass 1: row max and sum of exponentials
+    for (int j0 = 0; j0 < Sk16; j0 += 16) {
+      float s[2][4];
+      mma_a_yT(qa, sK, j0, lane, s);
+      float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + nb * 8 + 2 * t + e;
+          float ma = madd[j];
+          float a0 = ma, a1 = ma;
+          if (p.causal) {
+            if (j > i0 && a0 == 0.f) a0 = -10000.f;
+            if (j > i1 && a1 == 0.f) a1 = -10000.f;
+          }
+          s[nb][e] = s[nb][e] * p.scale + a0;
+          s[nb][2 + e] = s[nb][2 + e] * p.scale + a1;
+          cm0 = fmaxf(cm0, s[nb][e]);
+          cm1 = fmaxf(cm1, s[nb][2 + e]);
+        }
+      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+      const float n0 = fmaxf(m0, cm0), n1 = fmaxf(m1, cm1);
+      float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          e0 += __expf(s[nb][e] - n0);
+          e1 += __expf(s[nb][2 + e] - n1);
+        }
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 1);
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+      l0 = l0 * __expf(m0 - n0) + e0;
+      l1 = l1 * __expf(m1 - n1) + e1;
+      m0 = n0;
+      m1 = n1;
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    // pass 2: normalised probabilities -> P V
+    float o[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[nb][e] = 0.f;
+    for (int j0 = 0; j0 < Sk16; j0 += 16) {
+      float s[2][4];
+      mma_a_yT(qa, sK, j0, lane, s);
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int jb = j0 + nb * 8 + 2 * t;
+        bool k00 = true, k01 = true, k10 = true, k11 = true;
+        if (p.drop_on) {
+          keep_pair(p, bh, i0 < p.Sq ? i0 : 0, jb, Skq, k00, k01);
+          keep_pair(p, bh, i1 < p.Sq ? i1 : 0, jb, Skq, k10, k11);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = jb + e;
+          float ma = madd[j];
+          float a0 = ma, a1 = ma;
+          if (p.causal) {
+            if (j > i0 && a0 == 0.f) a0 = -10000.f;
+            if (j > i1 && a1 == 0.f) a1 = -10000.f;
+          }
+          float p0 = __expf(s[nb][e] * p.scale + a0 - m0) * inv0;
+          float p1 = __expf(s[nb][2 + e] * p.scale + a1 - m1) * inv1;
+          if (p.drop_on) {
+            p0 = (e == 0 ? k00 : k01) ? p0 * p.drop_scale : 0.f;
+            p1 = (e == 0 ? k10 : k11) ? p1 * p.drop_scale : 0.f;
+          }
+          s[nb][e] = p0;
+          s[nb][2 + e] = p1;
+        }
+      }
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[0][0], s[0][1]);
+      pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+      pa[2] = pack_bf16x2(s[1][0], s[1][1]);
+      pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+      mma_p_z(pa, sV, j0, lane, o);
+    }
+    // store context rows (heads merged: column h*64 + d) and the row log-sum-exp
+    bf16* orow0 = p.o + ((long long)seq * p.Sq + i0) * p.ldo + h * HD;
+    bf16* orow1 = p.o + ((long long)seq * p.Sq + i1) * p.ldo + h * HD;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      if (i0 < p.Sq) *reinterpret_cast<uint32_t*>(orow0 + nb * 8 + 2 * t) = pack_bf16x2(o[nb][0], o[nb][1]);
+      if (i1 < p.Sq) *reinterpret_cast<uint32_t*>(orow1 + nb * 8 + 2 * t) = pack_bf16x2(o[nb][2], o[nb][3]);
+    }
+    if (t == 0 && p.lse != nullptr) {
+      if (i0 < p.Sq) p.lse[bh * p.Sq + i0] = m0 + __logf(l0);
+      if (i1 < p.Sq) p.lse[bh * p.Sq + i1] = m1 + __logf(l1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_BWD_WARPS * 32)
+attention_bwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int Sq16 = (p.Sq + 15) & ~15, Sk16 = (p.Sk + 15) & ~15;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
+  bf16* sdO = sQ + Sq16 * LDS;
+  bf16* sK = sdO + Sq16 * LDS;
+  bf16* sV = sK + Sk16 * LDS;
+  float* madd = reinterpret_cast<float*>(sV + Sk16 * LDS);
+  float* sLse = madd + Sk16;
+  float* sD = sLse + Sq16;
+
+  const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const long long bh = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Skq = Sk16 >> 2;
+
+  load_head_tile(sQ, p.q + (long long)seq * p.Sq * p.ldq + h * HD, p.ldq, p.Sq, Sq16);
+  load_head_tile(sdO, p.d_o + (long long)seq * p.Sq * p.lddo + h * HD, p.lddo, p.Sq, Sq16);
+  load_head_tile(sK, p.k + (long long)seq * p.Sk * p.ldk + h * HD, p.ldk, p.Sk, Sk16);
+  load_head_tile(sV, p.v + (long long)seq * p.Sk * p.ldv + h * HD, p.ldv, p.Sk, Sk16);
+  build_key_mask(madd, p, seq, Sk16);
+  cp_async_wait_all();
+  __syncthreads();
+  // D_i = sum_d dO[i,d] * O[i,d]   (8 lanes per row, 8 dims each); LSE rows (+inf on padding -> P = 0)
+  for (int idx = threadIdx.x; idx < Sq16 * 8; idx += blockDim.x) {
+    const int r = idx >> 3, c = idx & 7;
+    float part = 0.f;
+    if (r < p.Sq) {
+      const uint4 uo = *reinterpret_cast<const uint4*>(p.o + ((long long)seq * p.Sq + r) * p.ldo + h * HD + c * 8);
+      const uint4 ud = *reinterpret_cast<const uint4*>(sdO + r * LDS + c * 8);
+      const uint32_t wo[4] = {uo.x, uo.y, uo.z, uo.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(wo[j]), b = unpack_bf16x2(wd[j]);
+        part += a.x * b.x + a.y * b.y;
+      }
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (c == 0) {
+      sD[r] = part;
+      sLse[r] = r < p.Sq ? p.lse[bh * p.Sq + r] : INFINITY;
+    }
+  }
+  __syncthreads();
+
+  const int nQ = Sq16 >> 4, nK = Sk16 >> 4;
+  for (int task = warp; task < nQ + nK; task += ATT_BWD_WARPS) {
+    if (task < nQ) {
+      // ---------------- dQ for 16 query rows ----------------
+      const int q0 = task * 16;
+      uint32_t qa[4][4], da[4][4];
+      load_a_frags(sQ, q0, lane, qa);
+      load_a_frags(sdO, q0, lane, da);
+      const int i0 = q0 + g, i1 = q0 + g + 8;
+      const float lse0 = sLse[i0], lse1 = sLse[i1], D0 = sD[i0], D1 = sD[i1];
+      float acc[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
+      for (int j0 = 0; j0 < Sk16; j0 += 16) {
+        float s[2][4], dp[2][4];
+        mma_a_yT(qa, sK, j0, lane, s);
+        mma_a_yT(da, sV, j0, lane, dp);
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          const int jb = j0 + nb * 8 + 2 * t;
+          bool k00 = true, k01 = true, k10 = true, k11 = true;
+          if (p.drop_on) {
+            keep_pair(p, bh, i0 < p.Sq ? i0 : 0, jb, Skq, k00, k01);
+            keep_pair(p, bh, i1 < p.Sq ? i1 : 0, jb, Skq, k10, k11);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = jb + e;
+            float ma = madd[j];
+            float a0 = ma, a1 = ma;
+            if (p.causal) {
+              if (j > i0 && a0 == 0.f) a0 = -10000.f;
+              if (j > i1 && a1 == 0.f) a1 = -10000.f;
+            }
+            const float p0 = __expf(s[nb][e] * p.scale + a0 - lse0);
+            const float p1 = __expf(s[nb][2 + e] * p.scale + a1 - lse1);
+            float g0 = dp[nb][e], g1 = dp[nb][2 + e];
+            if (p.drop_on) {
+              g0 = (e == 0 ? k00 : k01) ? g0 * p.drop_scale : 0.f;
+              g1 = (e == 0 ? k10 : k11) ? g1 * p.drop_scale : 0.f;
+            }
+            s[nb][e] = p0 * (g0 - D0) * p.scale;
+            s[nb][2 + e] = p1 * (g1 - D1) * p.scale;
+          }
+        }
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[0][0], s[0][1]);
+        pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+        pa[2] = pack_bf16x2(s[1][0], s[1][1]);
+        pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+        mma_p_z(pa, sK, j0, lane, acc);
+      }
+      bf16* r0 = p.dq + ((long long)seq * p.Sq + i0) * p.lddq + h * HD;
+      bf16* r1 = p.dq + ((long long)seq * p.Sq + i1) * p.lddq + h * HD;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        if (i0 < p.Sq) *reinterpret_cast<uint32_t*>(r0 + nb * 8 + 2 * t) = pack_bf16x2(acc[nb][0], acc[nb][1]);
+        if (i1 < p.Sq) *reinterpret_cast<uint32_t*>(r1 + nb * 8 + 2 * t) = pack_bf16x2(acc[nb][2], acc[nb][3]);
+      }
+    } else {
+      // ---------------- dK, dV for 16 key rows (transposed tiles) ----------------
+      const int k0 = (task - nQ) * 16;
+      uint32_t ka[4][4], va[4][4];
+      load_a_frags(sK, k0, lane, ka);
+      load_a_frags(sV, k0, lane, va);
+      const int j0r = k0 + g, j1r = k0 + g + 8;
+      const float ma0 = madd[j0r], ma1 = madd[j1r];
+      float dk[8][4], dv[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dk[nb][e] = dv[nb][e] = 0.f;
+      for (int q0 = 0; q0 < Sq16; q0 += 16) {
+        float st[2][4], dpt[2][4];
+        mma_a_yT(ka, sQ, q0, lane, st);    // S^T tile: rows = keys, cols = queries
+        mma_a_yT(va, sdO, q0, lane, dpt);  // dP^T tile
+        float pd[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = q0 + nb * 8 + 2 * t + e;
+            const float lse = sLse[i], D = sD[i];
+            float a0 = ma0, a1 = ma1;
+            if (p.causal) {
+              if (j0r > i && a0 == 0.f) a0 = -10000.f;
+              if (j1r > i && a1 == 0.f) a1 = -10000.f;
+            }
+            const float p0 = __expf(st[nb][e] * p.scale + a0 - lse);
+            const float p1 = __expf(st[nb][2 + e] * p.scale + a1 - lse);
+            float g0 = dpt[nb][e], g1 = dpt[nb][2 + e];
+            float pk0 = p0, pk1 = p1;
+            if (p.drop_on) {
+              const int ii = i < p.Sq ? i : 0;
+              const bool kp0 = keep_one(p, bh, ii, j0r, Skq), kp1 = keep_one(p, bh, ii, j1r, Skq);
+              g0 = kp0 ? g0 * p.drop_scale : 0.f;
+              g1 = kp1 ? g1 * p.drop_scale : 0.f;
+              pk0 = kp0 ? p0 * p.drop_scale : 0.f;
+              pk1 = kp1 ? p1 * p.drop_scale : 0.f;
+            }
+            pd[nb][e] = pk0;
+            pd[nb][2 + e] = pk1;
+            st[nb][e] = p0 * (g0 - D) * p.scale;
+            st[nb][2 + e] = p1 * (g1 - D) * p.scale;
+          }
+        uint32_t pa[4], sa[4];
+        pa[0] = pack_bf16x2(pd[0][0], pd[0][1]);
+        pa[1] = pack_bf16x2(pd[0][2], pd[0][3]);
+        pa[2] = pack_bf16x2(pd[1][0], pd[1][1]);
+        pa[3] = pack_bf16x2(pd[1][2], pd[1][3]);
+        sa[0] = pack_bf16x2(st[0][0], st[0][1]);
+        sa[1] = pack_bf16x2(st[0][2], st[0][3]);
+        sa[2] = pack_bf16x2(st[1][0], st[1][1]);
+        sa[3] = pack_bf16x2(st[1][2], st[1][3]);
+        mma_p_z(pa, sdO, q0, lane, dv);
+        mma_p_z(sa, sQ, q0, lane, dk);
+      }
+      bf16* kr0 = p.dk + ((long long)seq * p.Sk + j0r) * p.lddk + h * HD;
+      bf16* kr1 = p.dk + ((long long)seq * p.Sk + j1r) * p.lddk + h * HD;
+      bf16* vr0 = p.dv + ((long long)seq * p.Sk + j0r) * p.lddv + h * HD;
+      bf16* vr1 = p.dv + ((long long)seq * p.Sk + j1r) * p.lddv + h * HD;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        if (j0r < p.Sk) {
+          *reinterpret_cast<uint32_t*>(kr0 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][0], dk[nb][1]);
+          *reinterpret_cast<uint32_t*>(vr0 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][0], dv[nb][1]);
+        }
+        if (j1r < p.Sk) {
+          *reinterpret_cast<uint32_t*>(kr1 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][2], dk[nb][3]);
+          *reinterpret_cast<uint32_t*>(vr1 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][2], dv[nb][3]);
+        }
+      }
+    }
+  }
+}
+
+static int fill_common(AttnParams& p, const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                       long long ldv, const long long* mask_a, const long long* mask_b, int Wa, int Fb, int Nb,
+                       int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale, float p_drop,
+                       unsigned long long seed, unsigned long long stream_id) {
+  UNIVL_CHECK_ARG(q && k && v, "attention: null q/k/v");
+  UNIVL_CHECK_ARG(n_seq >= 0 && heads > 0 && Sq > 0 && Sk > 0 && Sq <= 256 && Sk <= 256,
+                  "attention: unsupported shape n_seq=%d heads=%d Sq=%d Sk=%d (S <= 256)", n_seq, heads, Sq, Sk);
+  UNIVL_CHECK_ARG((ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0, "attention: row strides must be multiples of 8");
+  UNIVL_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0,
+                  "attention: q/k/v must be 16-byte aligned");
+  UNIVL_CHECK_ARG(mask_a == nullptr || Wa + Fb == Sk, "attention: mask parts (%d + %d) must cover Sk=%d", Wa, Fb, Sk);
+  UNIVL_CHECK_ARG(!(Fb > 0 && mask_a != nullptr && mask_b == nullptr), "attention: missing second mask part");
+  UNIVL_CHECK_ARG(!all_pairs || Nb > 0, "attention: all_pairs needs Nb > 0");
+  UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "attention: bad dropout probability");
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv;
+  p.mask_a = mask_a; p.mask_b = mask_b; p.Wa = Wa; p.Fb = Fb; p.Nb = Nb > 0 ? Nb : 1; p.all_pairs = all_pairs;
+  p.n_seq = n_seq; p.heads = heads; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
+  p.drop_on = p_drop > 0.f;
+  p.drop_threshold = dropout_threshold(p_drop);
+  p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  p.seed = seed; p.stream = stream_id;
+  return UNIVL_OK;
+}
+
+}  // namespace univl
+
+using namespace univl;
+
+// ctx[T, heads*64] = softmax(Q K^T * scale + mask) V per (sequence, head).  q/k/v point at column 0 of head 0; head h
+// reads columns [h*64, h*64+64).  Key mask = concat(mask_a[i, :Wa], mask_b[j, :Fb]) (int64 0/1) with (i, j) = (seq, seq)
+// or, if all_pairs, (seq / Nb, seq % Nb); null mask_a = no padding mask.
+extern "C" int univl_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                   long long ldv, void* o, long long ldo, float* lse, const long long* mask_a,
+                                   const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq, int heads,
+                                   int Sq, int Sk, int causal, float scale, float p_drop, unsigned long long seed,
+                                   unsigned long long stream_id, void* stream) {
+  AttnParams p = {};
+  if (int rc = fill_common(p, q, ldq, k, ldk, v, ldv, mask_a, mask_b, Wa, Fb, Nb, all_pairs, n_seq, heads, Sq, Sk,
+                           causal, scale, p_drop, seed, stream_id))
+    return rc;
+  UNIVL_CHECK_ARG(o != nullptr && (ldo % 2) == 0, "attention_fwd: bad output");
+  if (n_seq == 0) return UNIVL_OK;
+  p.o = (bf16*)o; p.ldo = ldo; p.lse = lse;
+  const int Sq16 = (Sq + 15) & ~15, Sk16 = (Sk + 15) & ~15;
+  const size_t smem = (size_t)(Sq16 + 2 * Sk16) * LDS * 2 + (size_t)Sk16 * 4;
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_fwd smem attribute: %s", cudaGetErrorString(e));
+  attention_fwd_kernel<<<n_seq * heads, ATT_FWD_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  UNIVL_CHECK_LAUNCH("attention_fwd");
+  return UNIVL_OK;
+}
+
+extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                   long long ldv, const void* o, long long ldo, const float* lse, const void* d_o,
+                                   long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv,
+                                   long long lddv, const long long* mask_a, const long long* mask_b, int Wa, int Fb,
+                                   int Nb, int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale,
+                                   float p_drop, unsigned long long seed, unsigned long long stream_id, void* stream) {
+  AttnParams p = {};
+  if (int rc = fill_common(p, q, ldq, k, ldk, v, ldv, mask_a, mask_b, Wa, Fb, Nb, all_pairs, n_seq, heads, Sq, Sk,
+                           causal, scale, p_drop, seed, stream_id))
+    return rc;
+  UNIVL_CHECK_ARG(o && lse && d_o && dq && dk && dv, "attention_bwd: null pointer");
+  UNIVL_CHECK_ARG((ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 2) == 0 && (lddk % 2) == 0 && (lddv % 2) == 0,
+                  "attention_bwd: bad strides");
+  if (n_seq == 0) return UNIVL_OK;
+  p.o = (bf16*)const_cast<void*>(o); p.ldo = ldo; p.lse = const_cast<float*>(lse);
+  p.d_o = (const bf16*)d_o; p.lddo = lddo;
+  p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
+  p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  const int Sq16 = (Sq + 15) & ~15, Sk16 = (Sk + 15) & ~15;
+  const size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16) * 4;
+  cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_bwd smem attribute: %s", cudaGetErrorString(e));
+  attention_bwd_kernel<<<n_seq * heads, ATT_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  UNIVL_CHECK_LAUNCH("attention_bwd");
+  return UNIVL_OK;
+}

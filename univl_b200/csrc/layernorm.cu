@@ -1,0 +1,313 @@
+// univl_b200 — fused (dropout + residual +) LayerNorm, forward and backward.  HBM-bound.
+//
+// Reference semantics (modules/until_module.py:49-53): y = gamma * (z - mean) / sqrt(var_biased + eps) + beta with
+// eps = 1e-12 INSIDE the sqrt.  The fused forms cover
+//   BertSelfOutput / BertOutput (modules/module_bert.py:207-211, :246-250):  y = LN(dropout(x) + residual)
+//   embeddings (module_bert.py:143-145 etc.):                               y = dropout(LN(z))        (drop_mode 2)
+//   prediction-head transform (module_bert.py:308-312) and NormalizeVideo (modeling.py:88-92, fp32 input).
+// One warp owns one row at a time (cols <= 1024, cols % 256 == 0 -> 1..4 16-byte vectors per lane); all statistics are
+// fp32 and two-pass over registers, exactly the reference's mean -> centred variance order.  Backward regenerates the
+// dropout mask from (seed, stream) and accumulates dgamma / dbeta / dbias column sums in registers across the rows a
+// warp walks, then reduces through shared memory and issues one atomicAdd per column per CTA.
+#include "common.cuh"
+
+namespace univl {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAX_VEC = 4;  // cols <= 1024
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+struct DropCfg {
+  int mode;  // 0 none, 1 on x before the residual add, 2 on the LayerNorm output
+  uint32_t threshold;
+  float scale;  // 1/(1-p)
+  uint64_t seed, stream;
+};
+
+// keep flags of 8 consecutive elements starting at flat index idx0 (idx0 % 8 == 0): two Philox calls
+__device__ __forceinline__ void keep8(const DropCfg& d, uint64_t idx0, bool (&k)[8]) {
+  const uint4 r0 = philox4x32(d.seed, d.stream, idx0 >> 2);
+  const uint4 r1 = philox4x32(d.seed, d.stream, (idx0 >> 2) + 1);
+  k[0] = r0.x < d.threshold; k[1] = r0.y < d.threshold; k[2] = r0.z < d.threshold; k[3] = r0.w < d.threshold;
+  k[4] = r1.x < d.threshold; k[5] = r1.y < d.threshold; k[6] = r1.z < d.threshold; k[7] = r1.w < d.threshold;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int cols, float eps, DropCfg drop) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = cols >> 8;
+  const float inv_cols = 1.0f / (float)cols;
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+    float z[LN_MAX_VEC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 8;
+        load8(x + row * cols + c, z[i]);
+        if (drop.mode == 1) {
+          bool k[8];
+          keep8(drop, (uint64_t)row * cols + c, k);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[i][j] = k[j] ? z[i][j] * drop.scale : 0.f;
+        }
+        if (res != nullptr) {
+          float r[8];
+          load8(res + row * cols + c, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[i][j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += z[i][j];
+      }
+    }
+    const float mean = warp_sum(s) * inv_cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = z[i][j] - mean;
+          q += d * d;
+        }
+      }
+    const float var = warp_sum(q) * inv_cols;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 8;
+        float g[8], b[8], o[8];
+        load8(gamma + c, g);
+        load8(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j] * ((z[i][j] - mean) * rstd) + b[j];
+        if (drop.mode == 2) {
+          bool k[8];
+          keep8(drop, (uint64_t)row * cols + c, k);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = k[j] ? o[j] * drop.scale : 0.f;
+        }
+        store8(y + row * cols + c, o);
+      }
+  }
+}
+
+// Backward.  dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy_eff * gamma.
+//   dx_res   (bf16, may be null): dz                       — gradient w.r.t. the residual input (and x when no dropout)
+//   dx_dense (bf16, may be null): dz * keep/(1-p)          — gradient w.r.t. x under drop_mode 1
+//   dgamma, dbeta (fp32, atomically accumulated), dbias (fp32, optional) += column sums of dx_dense (or dz)
+template <typename TIn>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const TIn* __restrict__ x,
+                     const bf16* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, bf16* __restrict__ dx_res, bf16* __restrict__ dx_dense,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int rows,
+                     int cols, DropCfg drop) {
+  __shared__ float red[LN_WARPS][32 * 8 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = cols >> 8;
+  const float inv_cols = 1.0f / (float)cols;
+  float acc_g[LN_MAX_VEC][8], acc_b[LN_MAX_VEC][8], acc_x[LN_MAX_VEC][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = acc_x[i][j] = 0.f;
+
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[LN_MAX_VEC][8], g[LN_MAX_VEC][8];
+    bool keep[LN_MAX_VEC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 8;
+        float z[8], d[8], gm[8];
+        load8(x + row * cols + c, z);
+        if (drop.mode != 0) keep8(drop, (uint64_t)row * cols + c, keep[i]);
+        if (drop.mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = keep[i][j] ? z[j] * drop.scale : 0.f;
+        }
+        if (res != nullptr) {
+          float r[8];
+          load8(res + row * cols + c, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] += r[j];
+        }
+        load8(dy + row * cols + c, d);
+        if (dy2 != nullptr) {
+          float d2[8];
+          load8(dy2 + row * cols + c, d2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] += d2[j];
+        }
+        if (drop.mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = keep[i][j] ? d[j] * drop.scale : 0.f;
+        }
+        load8(gamma + c, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (z[j] - mean) * rstd;
+          g[i][j] = d[j] * gm[j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          acc_g[i][j] += d[j] * xh[i][j];
+          acc_b[i][j] += d[j];
+        }
+      }
+    s1 = warp_sum(s1) * inv_cols;
+    s2 = warp_sum(s2) * inv_cols;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (i < nvec) {
+        const int c = (i * 32 + lane) * 8;
+        float dz[8], dd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dz[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+          dd[j] = (drop.mode == 1) ? (keep[i][j] ? dz[j] * drop.scale : 0.f) : dz[j];
+          acc_x[i][j] += dd[j];
+        }
+        if (dx_res != nullptr) store8(dx_res + row * cols + c, dz);
+        if (dx_dense != nullptr && dx_dense != dx_res) store8(dx_dense + row * cols + c, dd);
+      }
+  }
+  // column sums: reduce the LN_WARPS partials through shared memory, one vector slot at a time
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
+    if (dst == nullptr) continue;
+    for (int i = 0; i < nvec; ++i) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        red[warp][lane * 8 + j] = which == 0 ? acc_g[i][j] : which == 1 ? acc_b[i][j] : acc_x[i][j];
+      __syncthreads();
+      for (int e = threadIdx.x; e < 256; e += LN_WARPS * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) t += red[w][e];
+        atomicAdd(dst + i * 256 + e, t);
+      }
+    }
+  }
+}
+
+static int check_ln_shape(const char* what, int rows, int cols) {
+  UNIVL_CHECK_ARG(rows >= 0 && cols > 0 && (cols % 256) == 0 && cols <= 256 * LN_MAX_VEC,
+                  "%s: cols must be a multiple of 256 and <= %d (got rows=%d cols=%d)", what, 256 * LN_MAX_VEC, rows,
+                  cols);
+  return UNIVL_OK;
+}
+
+static DropCfg make_drop(int mode, float p, unsigned long long seed, unsigned long long stream) {
+  DropCfg d;
+  d.mode = (p > 0.f) ? mode : 0;
+  d.threshold = dropout_threshold(p);
+  d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
+  d.seed = seed;
+  d.stream = stream;
+  return d;
+}
+
+static int ln_grid(int rows) {
+  long long blocks = ((long long)rows + LN_WARPS - 1) / LN_WARPS;
+  const long long cap = 148LL * 8;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace univl
+
+using namespace univl;
+
+// y = LN(dropout(x) + res) [drop_mode 1]  or  dropout(LN(x + res)) [drop_mode 2];  x, res, y bf16; stats fp32.
+extern "C" int univl_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                                   float* mean, float* rstd, int rows, int cols, float eps, float p_drop,
+                                   int drop_mode, unsigned long long seed, unsigned long long stream_id,
+                                   void* stream) {
+  if (int rc = check_ln_shape("layernorm_fwd", rows, cols)) return rc;
+  UNIVL_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
+  UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && drop_mode >= 0 && drop_mode <= 2, "layernorm_fwd: bad dropout");
+  if (rows == 0) return UNIVL_OK;
+  layernorm_fwd_kernel<bf16><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
+      make_drop(drop_mode, p_drop, seed, stream_id));
+  UNIVL_CHECK_LAUNCH("layernorm_fwd");
+  return UNIVL_OK;
+}
+
+extern "C" int univl_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* res,
+                                   const float* gamma, const float* mean, const float* rstd, void* dx_res,
+                                   void* dx_dense, float* dgamma, float* dbeta, float* dbias, int rows, int cols,
+                                   float p_drop, int drop_mode, unsigned long long seed,
+                                   unsigned long long stream_id, void* stream) {
+  if (int rc = check_ln_shape("layernorm_bwd", rows, cols)) return rc;
+  UNIVL_CHECK_ARG(dy && x && gamma && mean && rstd, "layernorm_bwd: null pointer");
+  UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && drop_mode >= 0 && drop_mode <= 2, "layernorm_bwd: bad dropout");
+  if (rows == 0) return UNIVL_OK;
+  layernorm_bwd_kernel<bf16><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)dy2, (const bf16*)x, (const bf16*)res, gamma, mean, rstd, (bf16*)dx_res,
+      (bf16*)dx_dense, dgamma, dbeta, dbias, rows, cols, make_drop(drop_mode, p_drop, seed, stream_id));
+  UNIVL_CHECK_LAUNCH("layernorm_bwd");
+  return UNIVL_OK;
+}
+
+// fp32 input rows (NormalizeVideo, reference modules/modeling.py:88-92): y(bf16) = LN(x_f32); no dropout.
+extern "C" int univl_layernorm_f32_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean,
+                                       float* rstd, int rows, int cols, float eps, void* stream) {
+  if (int rc = check_ln_shape("layernorm_f32_fwd", rows, cols)) return rc;
+  UNIVL_CHECK_ARG(x && gamma && beta && y, "layernorm_f32_fwd: null pointer");
+  if (rows == 0) return UNIVL_OK;
+  layernorm_fwd_kernel<float><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      x, nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps, make_drop(0, 0.f, 0, 0));
+  UNIVL_CHECK_LAUNCH("layernorm_f32_fwd");
+  return UNIVL_OK;
+}
+
+// parameter gradients only (the video features are inputs, not activations)
+extern "C" int univl_layernorm_f32_bwd(const void* dy, const float* x, const float* gamma, const float* mean,
+                                       const float* rstd, float* dgamma, float* dbeta, int rows, int cols,
+                                       void* stream) {
+  if (int rc = check_ln_shape("layernorm_f32_bwd", rows, cols)) return rc;
+  UNIVL_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta, "layernorm_f32_bwd: null pointer");
+  if (rows == 0) return UNIVL_OK;
+  layernorm_bwd_kernel<float><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, nullptr, x, nullptr, gamma, mean, rstd, nullptr, nullptr, dgamma, dbeta, nullptr, rows, cols,
+      make_drop(0, 0.f, 0, 0));
+  UNIVL_CHECK_LAUNCH("layernorm_f32_bwd");
+  return UNIVL_OK;
+}

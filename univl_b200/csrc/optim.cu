@@ -1,0 +1,132 @@
+// univl_b200 — fused multi-tensor BertAdam over flat fp32 buffers.  HBM-bound: one read of
+// p/g/m/v, one write of p/m/v plus the bf16 weight copy the GEMMs consume — 3 launches for ~300 tensors instead
+// of the reference's Python loop of ~10 launches per tensor.
+//
+// Reference semantics restated (modules/optimization.py:103-167, driver main_task_retrieval.py:347):
+//   driver : clip_grad_norm_(all parameters, 1.0)             -> g *= min(1, 1 / (||g||_all + 1e-6))
+//   step   : per tensor clip_grad_norm_(p, max_grad_norm)     -> g *= min(1, max / (||g_t|| + 1e-6))
+//            m = b1 m + (1-b1) g ;  v = b2 v + (1-b2) g^2     (NO bias correction)
+//            update = m / (sqrt(v) + e) + weight_decay * p    (e OUTSIDE the sqrt, decoupled decay)
+//            p -= lr * schedule(step / t_total, warmup) * update ;  step += 1
+//   warmup_linear(x, w) = x / w if x < w else max((x - 1) / (w - 1), 0)      (optimization.py:37-43)
+// The step counter lives in device memory so the whole update is CUDA-graph capturable.
+#include "common.cuh"
+
+namespace univl {
+
+struct AdamSeg {  // one per tensor, 32 bytes
+  long long offset;
+  long long count;
+  float lr;
+  float weight_decay;
+  float pad0, pad1;
+};
+
+struct AdamCfg {
+  float b1, b2, eps;
+  float max_grad_norm;     // per-tensor clip (<= 0 disables)
+  float global_clip_norm;  // all-parameter clip (<= 0 disables)
+  float warmup;            // fraction of t_total, < 0 = none
+  long long t_total;       // < 0 = constant lr
+  float grad_scale;        // e.g. 1 / world_size after a sum all-reduce
+};
+
+__global__ void __launch_bounds__(256)
+adam_sumsq_kernel(const float* __restrict__ g, const AdamSeg* __restrict__ segs, float* __restrict__ sumsq,
+                  float grad_scale) {
+  __shared__ float red[8];
+  const AdamSeg s = segs[blockIdx.y];
+  const float* gp = g + s.offset;
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += stride) {
+    const float x = gp[i] * grad_scale;
+    acc += x * x;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    if (t != 0.f) atomicAdd(sumsq + blockIdx.y, t);
+  }
+}
+
+// sumsq[n_tensors] -> sumsq[n_tensors] holds the total
+__global__ void adam_total_kernel(float* __restrict__ sumsq, int n_tensors) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_tensors; i += blockDim.x) acc += sumsq[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    sumsq[n_tensors] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   bf16* __restrict__ p_bf16, const AdamSeg* __restrict__ segs, const float* __restrict__ sumsq,
+                   int n_tensors, const long long* __restrict__ step, AdamCfg cfg) {
+  const AdamSeg s = segs[blockIdx.y];
+  // a tensor whose gradient is identically zero received none this step (unused poolers etc.): the reference
+  // skips parameters with `p.grad is None` entirely — no moment update, no weight decay (optimization.py:115-116)
+  if (sumsq[blockIdx.y] == 0.f) return;
+  float cg = 1.f;
+  if (cfg.global_clip_norm > 0.f) cg = fminf(1.f, cfg.global_clip_norm / (sqrtf(sumsq[n_tensors]) + 1e-6f));
+  float ct = 1.f;
+  if (cfg.max_grad_norm > 0.f) ct = fminf(1.f, cfg.max_grad_norm / (cg * sqrtf(sumsq[blockIdx.y]) + 1e-6f));
+  const float gmul = cfg.grad_scale * cg * ct;
+  float sched = 1.f;
+  if (cfg.t_total > 0) {
+    const float x = (float)((double)(*step) / (double)cfg.t_total);
+    sched = (cfg.warmup >= 0.f && x < cfg.warmup) ? x / cfg.warmup : fmaxf((x - 1.f) / (cfg.warmup - 1.f), 0.f);
+  }
+  const float lr = s.lr * sched;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += stride) {
+    const long long e = s.offset + i;
+    const float gr = g[e] * gmul;
+    const float mm = cfg.b1 * m[e] + (1.f - cfg.b1) * gr;
+    const float vv = cfg.b2 * v[e] + (1.f - cfg.b2) * gr * gr;
+    float pp = p[e];
+    const float upd = mm / (sqrtf(vv) + cfg.eps) + s.weight_decay * pp;
+    pp -= lr * upd;
+    m[e] = mm;
+    v[e] = vv;
+    p[e] = pp;
+    if (p_bf16 != nullptr) p_bf16[e] = __float2bfloat16(pp);
+  }
+}
+
+__global__ void adam_step_inc_kernel(long long* step) { *step += 1; }
+
+}  // namespace univl
+
+using namespace univl;
+
+// One optimizer step over flat buffers.  segs: device array of n_tensors {offset, count, lr, weight_decay, -, -};
+// scratch: n_tensors + 1 floats; step: device int64 (incremented).  p_bf16 (same element offsets as p) may be null.
+extern "C" int univl_bert_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const void* segs,
+                                    int n_tensors, float* scratch, long long* step, float b1, float b2, float eps,
+                                    float max_grad_norm, float global_clip_norm, float warmup, long long t_total,
+                                    float grad_scale, int blocks_per_tensor, void* stream) {
+  UNIVL_CHECK_ARG(p && g && m && v && segs && scratch && step, "bert_adam_step: null pointer");
+  UNIVL_CHECK_ARG(n_tensors > 0 && n_tensors <= 65535 && blocks_per_tensor > 0, "bert_adam_step: bad tensor count");
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamCfg cfg{b1, b2, eps, max_grad_norm, global_clip_norm, warmup, t_total, grad_scale};
+  const AdamSeg* s = reinterpret_cast<const AdamSeg*>(segs);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)(n_tensors + 1) * sizeof(float), st);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "bert_adam_step memset: %s", cudaGetErrorString(e));
+  adam_sumsq_kernel<<<dim3(blocks_per_tensor, n_tensors), 256, 0, st>>>(g, s, scratch, grad_scale);
+  adam_total_kernel<<<1, 256, 0, st>>>(scratch, n_tensors);
+  adam_update_kernel<<<dim3(blocks_per_tensor, n_tensors), 256, 0, st>>>(p, g, m, v, (bf16*)p_bf16, s, scratch,
+                                                                         n_tensors, step, cfg);
+  adam_step_inc_kernel<<<1, 1, 0, st>>>(step);
+  UNIVL_CHECK_LAUNCH("bert_adam_step");
+  return UNIVL_OK;
+}

@@ -17,49 +17,32 @@ c_ull = ctypes.c_ulonglong
 c_f = ctypes.c_float
 c_p = ctypes.c_void_p
 
-# name -> argtypes; every entry returns int (0 = ok) unless listed in _SPECIAL.
-SIGNATURES = {
-    "univl_gemm_bf16": [c_p, c_ll, c_int, c_p, c_ll, c_int, c_int, c_int, c_int, c_p, c_ll, c_int, c_p, c_p, c_ll,
-                        c_p, c_ll, c_f, c_int, c_int, c_p],
-    "univl_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_f, c_ull, c_ull, c_p],
-    "univl_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_ull,
-                            c_ull, c_p],
-    "univl_layernorm_f32_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_p],
-    "univl_layernorm_f32_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p],
-    "univl_embed_text_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p],
-    "univl_embed_text_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p],
-    "univl_embed_cross_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
-    "univl_embed_cross_bwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
-    "univl_add_pos_fwd": [c_p, c_p, c_p, c_int, c_int, c_int, c_p],
-    "univl_add_pos_bwd": [c_p, c_p, c_int, c_int, c_int, c_p],
-    "univl_attention_fwd": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_p, c_int, c_int, c_int, c_int, c_int,
-                            c_int, c_f, c_f, c_ull, c_ull, c_p],
-    "univl_attention_bwd": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll,
-                            c_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_f, c_ull, c_ull, c_p],
-    "univl_colsum_bf16": [c_p, c_ll, c_p, c_int, c_int, c_p],
-    "univl_cast_f32_to_bf16": [c_p, c_p, c_ll, c_p],
-    "univl_multi_cast_f32_to_bf16": [c_p, c_p, c_p, c_int, c_p],
-    "univl_gather_rows_bf16": [c_p, c_ll, c_p, c_p, c_ll, c_int, c_int, c_p],
-    "univl_scatter_add_rows_bf16": [c_p, c_ll, c_p, c_p, c_ll, c_int, c_int, c_p],
-    "univl_meanpool_fwd": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
-    "univl_meanpool_bwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
-    "univl_sim_matmul_fwd": [c_p, c_p, c_p, c_int, c_int, c_int, c_p],
-    "univl_sim_matmul_bwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p],
-    "univl_maxmargin_loss": [c_p, c_p, c_p, c_p, c_int, c_f, c_f, c_p],
-    "univl_crossen_loss": [c_p, c_p, c_p, c_int, c_f, c_p],
-    "univl_milnce_loss": [c_p, c_p, c_p, c_int, c_int, c_f, c_p],
-    "univl_softmax_xent": [c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_int, c_int, c_int, c_f, c_p],
-    "univl_mfm_nce_loss": [c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_int, c_f, c_p],
-    "univl_pooler_tanh_fwd": [c_p, c_p, c_ll, c_p],
-    "univl_pooler_tanh_bwd": [c_p, c_p, c_p, c_ll, c_p],
-    "univl_bert_adam_step": [c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_p],
-    "univl_grad_sqnorm": [c_p, c_ll, c_p, c_p],
-    "univl_fill_f32": [c_p, c_f, c_ll, c_p],
-}
-_SPECIAL = {
-    "univl_last_error_string": (ctypes.c_char_p, []),
-    "univl_abi_version": (c_int, []),
-}
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "univl_b200.h")
+
+
+def _ctype_of(decl):
+    """Map one C parameter declaration of include/univl_b200.h to a ctypes type."""
+    decl = decl.strip()
+    if "*" in decl:
+        return c_p
+    base = " ".join(decl.split()[:-1]) if len(decl.split()) > 1 else decl
+    base = base.replace("const", "").strip()
+    return {"int": c_int, "float": c_f, "long long": c_ll, "unsigned long long": c_ull}[base]
+
+
+def parse_header(path=HEADER_PATH):
+    """{name: (restype, [argtypes])} for every function the header declares — the single source of truth for the
+    binding, so the ctypes signatures cannot drift from the C ABI."""
+    import re
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"(const char\*|int)\s+(univl_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        argtypes = [] if args in ("", "void") else [_ctype_of(a) for a in args.split(",")]
+        out[name] = (ctypes.c_char_p if "char" in ret else c_int, argtypes)
+    return out
+
 
 _lib = None
 _lock = threading.Lock()
@@ -80,15 +63,11 @@ def load(build_if_missing=False):
                     "univl_b200: %s is missing — run `python -m univl_b200.build` (or __graft_entry__.build()); "
                     "there is no fallback compute path" % LIB_PATH)
         lib = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _SPECIAL.items():
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
-        for name, args in SIGNATURES.items():
+        for name, (res, args) in parse_header().items():
             fn = getattr(lib, name, None)
             if fn is None:
-                continue
-            fn.restype = c_int
+                raise RuntimeError("univl_b200: %s does not export %s (stale build?)" % (LIB_PATH, name))
+            fn.restype = res
             fn.argtypes = args
         _lib = lib
         return lib

@@ -1,0 +1,191 @@
+"""Per-model device runtime: bf16 weight arena, dropout RNG streams, kernel-launch counter.
+
+The fp32 `nn.Parameter`s keep the reference's names, shapes and tying; the tensor-core
+kernels consume bf16 copies that live in ONE flat arena per model.  The copies are derived state — never in
+`state_dict()` — refreshed by a single multi-tensor cast launch at each top-level entry (the reference's BertAdam
+updates weights through `p.data`, which bumps no version counter, so staleness cannot be detected cheaply), unless a
+fused optimizer step that writes the arena itself has marked it fresh.  query/key/value weights of one attention
+block are laid out adjacently so the fused QKV projection reads them as one [2304, 768] matrix without a repack.
+"""
+import threading
+
+import torch
+
+from . import lib
+
+_tls = threading.local()
+_launches = [0]
+
+
+def count_launches(n=1):
+    _launches[0] += n
+
+
+def launch_count():
+    return _launches[0]
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """C-ABI call on the current stream (the stream argument is always last)."""
+    count_launches()
+    return lib.call(name, *args, stream_ptr())
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class WeightArena:
+    """bf16 shadow copies of every >=2-D parameter of a module tree, in one flat buffer."""
+
+    def __init__(self, root):
+        self.root = root
+        self.device = None
+        self.entries = []      # (param, offset, numel)
+        self.by_id = {}        # id(param) -> (offset, shape)
+        self.packed = {}       # (id(q), id(k), id(v)) -> (offset, rows, cols)
+        self.buf = None
+        self.table = None
+        self._ptrs = None
+        self.fresh = False
+        self.seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        self.stream_counter = 0
+
+    # ---- layout -----------------------------------------------------------------------------------------
+    def _build(self, device):
+        seen = set()
+        order = []
+        # attention blocks first: q, k, v weights adjacent
+        for mod in self.root.modules():
+            trio = getattr(mod, "_qkv_modules", None)
+            if trio is None:
+                continue
+            ws = [m.weight for m in trio()]
+            if all(id(w) not in seen for w in ws):
+                for w in ws:
+                    seen.add(id(w))
+                    order.append(w)
+                self.packed[tuple(id(w) for w in ws)] = len(order) - 3
+        for p in self.root.parameters():
+            if id(p) in seen or p.dim() < 2:
+                continue
+            seen.add(id(p))
+            order.append(p)
+        off = 0
+        offsets = []
+        for p in order:
+            offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64  # 128-byte aligned slots
+        self.buf = torch.empty(off, dtype=torch.bfloat16, device=device)
+        self.entries = [(p, o, p.numel()) for p, o in zip(order, offsets)]
+        self.by_id = {id(p): (o, tuple(p.shape)) for p, o in zip(order, offsets)}
+        for key, first in list(self.packed.items()):
+            p0 = order[first]
+            contiguous = all(offsets[first + i + 1] == offsets[first + i] + order[first + i].numel() for i in range(2))
+            assert contiguous, "qkv weights must be adjacent in the arena"
+            self.packed[key] = (offsets[first], 3 * p0.shape[0], p0.shape[1])
+        self.device = device
+        self._ptrs = None
+
+    def _sync_table(self):
+        ptrs = [p.data_ptr() for p, _, _ in self.entries]
+        if ptrs == self._ptrs:
+            return
+        base = self.buf.data_ptr()
+        rows = [[pp, base + 2 * o, n] for pp, (_, o, n) in zip(ptrs, self.entries)]
+        # uint64 values fit int64 for device addresses
+        self.table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        self._ptrs = ptrs
+
+    def prepare(self, device):
+        if self.buf is None or self.device != device:
+            self._build(device)
+        for p, _, _ in self.entries:
+            if p.device != device:
+                raise RuntimeError("univl_b200: parameters moved off %s; call model.to(device) before use" % device)
+            if p.dtype != torch.float32:
+                raise RuntimeError("univl_b200: parameters must stay fp32 (got %s)" % p.dtype)
+        if not self.fresh:
+            self._sync_table()
+            call("univl_multi_cast_f32_to_bf16", self.table.data_ptr(), len(self.entries), 16)
+        self.fresh = False
+
+    # ---- lookup ------------------------------------------------------------------------------------------
+    def bf16(self, param):
+        off, shape = self.by_id[id(param)]
+        n = 1
+        for s in shape:
+            n *= s
+        return self.buf[off:off + n].view(shape)
+
+    def bf16_qkv(self, q, k, v):
+        off, rows, cols = self.packed[(id(q), id(k), id(v))]
+        return self.buf[off:off + rows * cols].view(rows, cols)
+
+    def next_stream(self):
+        self.stream_counter += 1
+        return self.stream_counter
+
+
+def arena_of(root):
+    a = root.__dict__.get("_univl_arena")
+    if a is None:
+        a = WeightArena(root)
+        root.__dict__["_univl_arena"] = a
+    return a
+
+
+class use_model:
+    """Context manager for a top-level entry: prepares the arena of `root` on `device` and makes it current."""
+
+    def __init__(self, root, device):
+        self.root, self.device = root, device
+
+    def __enter__(self):
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "univl_b200 runs on CUDA (sm_100a) only — there is no CPU path; move the model and inputs to a "
+                "B200 (got device %s)" % self.device)
+        prev = getattr(_tls, "arena", None)
+        self.prev = prev
+        if prev is not None and prev.root is not self.root and _covers(prev, self.root):
+            self.arena = prev  # nested entry of a sub-model whose parameters the outer arena already covers
+        else:
+            self.arena = arena_of(self.root)
+            if prev is None or prev is not self.arena:
+                with torch.cuda.device(self.device):
+                    self.arena.prepare(self.device)
+        _tls.arena = self.arena
+        return self.arena
+
+    def __exit__(self, *exc):
+        _tls.arena = self.prev
+        return False
+
+
+def _covers(arena, root):
+    for p in root.parameters():
+        if p.dim() >= 2 and id(p) not in arena.by_id:
+            return False
+    return arena.buf is not None
+
+
+def set_grad_sink(flat, model):
+    """register (or clear) the flat gradient buffers the backward kernels accumulate into directly"""
+    model.__dict__["_univl_sink"] = flat
+
+
+def current_sink():
+    a = getattr(_tls, "arena", None)
+    return None if a is None else a.root.__dict__.get("_univl_sink")
+
+
+def current():
+    a = getattr(_tls, "arena", None)
+    if a is None:
+        raise RuntimeError("univl_b200: no active model context (internal error)")
+    return a
