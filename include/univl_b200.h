@@ -133,10 +133,10 @@ int univl_pooler_sim_bwd(const void* u, const float* w, const float* dout, void*
                          int H, void* stream);
 
 /* ---- optimizer (modules/optimization.py:103-167 + driver clip main_task_retrieval.py:347) --------------------- */
-int univl_bert_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const void* segs, int n_tensors,
-                         float* scratch, long long* step, float b1, float b2, float eps, float max_grad_norm,
-                         float global_clip_norm, float warmup, long long t_total, float grad_scale,
-                         int blocks_per_tensor, void* stream);
+int univl_bert_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const void* segs, int n_chunks,
+                         int n_tensors, float* scratch, long long* step, float b1, float b2, float eps,
+                         float max_grad_norm, float global_clip_norm, float warmup, long long t_total,
+                         float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

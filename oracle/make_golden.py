@@ -29,6 +29,9 @@ CASES = {
     "cfg1_ft_joint": (dict(mode="ft_joint", batch_size=4), dict(seed=1234, ragged=True)),
     "cfg1_ft_joint_fixedlen": (dict(mode="ft_joint", batch_size=4), dict(seed=1235, ragged=False)),
     "cfg1_ft_align": (dict(mode="ft_align", batch_size=4), dict(seed=1234, ragged=True)),
+    # the same two with the reference's own init law (N(0,0.02), zero biases, unit LN): "random-init bert-base"
+    "cfg1_ft_joint_init": (dict(mode="ft_joint", batch_size=4), dict(seed=1234, ragged=True), dict(init_law=True)),
+    "cfg1_ft_align_init": (dict(mode="ft_align", batch_size=4), dict(seed=1234, ragged=True), dict(init_law=True)),
     "ft_joint_npair2": (dict(mode="ft_joint", batch_size=3, n_pair=2, text_layers=2, visual_layers=1, max_words=16,
                              max_frames=12), dict(seed=7, ragged=True)),
     "caption_small": (dict(mode="caption", batch_size=2, text_layers=2, visual_layers=1, cross_layers=1,
@@ -72,8 +75,8 @@ def build_reference_model(cfg, state_dict):
     return model
 
 
-def run_reference(cfg, batch_kwargs, seed=0):
-    sd = synth.make_state_dict(cfg, seed=seed)
+def run_reference(cfg, batch_kwargs, seed=0, weight_kwargs=None):
+    sd = synth.make_state_dict(cfg, seed=seed, **(weight_kwargs or {}))
     model = build_reference_model(cfg, sd)
     # every synthetic key must have landed (no silent "missing key" in the non-strict loader)
     msd = model.state_dict()
@@ -120,12 +123,14 @@ def summarise(t):
 
 
 def make_case(name):
-    cfg_kw, batch_kw = CASES[name]
+    case = CASES[name]
+    cfg_kw, batch_kw = case[0], case[1]
+    weight_kw = case[2] if len(case) > 2 else {}
     cfg = synth.task_config(**cfg_kw)
-    model, sd, batch, loss, cap, grads = run_reference(cfg, batch_kw)
+    model, sd, batch, loss, cap, grads = run_reference(cfg, batch_kw, weight_kwargs=weight_kw)
     seq, vis = cap["seq"][0], cap["vis"][0]
     gold = dict(
-        name=name, cfg_kwargs=cfg_kw, batch_kwargs=batch_kw, weight_seed=0, loss=loss,
+        name=name, cfg_kwargs=cfg_kw, batch_kwargs=batch_kw, weight_seed=0, weight_kwargs=weight_kw, loss=loss,
         torch_version=torch.__version__,
         sim_matrices=[s.float() for s in cap.get("sim_matrices", [])],
         seq_slice=seq[:, :6, :16].clone(), vis_slice=vis[:, :6, :16].clone(),

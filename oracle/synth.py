@@ -139,8 +139,10 @@ def state_dict_spec(cfg):
     return spec
 
 
-def make_state_dict(cfg, seed=0, weight_std=0.04, dtype=torch.float32):
+def make_state_dict(cfg, seed=0, weight_std=0.04, dtype=torch.float32, init_law=False):
     """Deterministic non-trivial weights: N(0, weight_std) matrices, LayerNorm gains 1 + 0.1 N(0,1), biases 0.02 N(0,1).
+    `init_law=True` instead follows the reference's own initialisation (modules/until_module.py:70-85): N(0, 0.02)
+    matrices / embedding tables, zero biases, unit LayerNorm gains — BASELINE.json configs[0] "random-init bert-base".
 
     Each tensor draws from its own generator seeded by (seed, index) so the values do not depend on which other
     tensors a mode contains.  Aliases of tied tensors are added as extra keys sharing storage.
@@ -149,11 +151,11 @@ def make_state_dict(cfg, seed=0, weight_std=0.04, dtype=torch.float32):
     for idx, (key, shape) in enumerate(state_dict_spec(cfg)):
         g = torch.Generator().manual_seed(seed * 100003 + _stable_hash(key))
         if key.endswith("LayerNorm.weight") or key.endswith("visual_norm2d.weight"):
-            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            t = torch.ones(shape) if init_law else 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif len(shape) == 1:
-            t = 0.02 * torch.randn(shape, generator=g)
+            t = torch.zeros(shape) if init_law else 0.02 * torch.randn(shape, generator=g)
         else:
-            t = weight_std * torch.randn(shape, generator=g)
+            t = (0.02 if init_law else weight_std) * torch.randn(shape, generator=g)
         sd[key] = t.to(dtype)
     for alias, owner in tied_keys(cfg).items():
         sd[alias] = sd[owner]

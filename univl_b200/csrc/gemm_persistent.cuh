@@ -1,0 +1,301 @@
+// univl_b200 — persistent, warp-specialised tcgen05 GEMM (included by gemm_tcgen05.cu).
+//
+// Same math and operand conventions as gemm_tcgen05_kernel, restructured so the tensor pipe never waits for the
+// epilogue:
+//   * grid = min(#work items, #SMs); each CTA walks work items (m-tile fastest, then n-tile, then k-split) round-robin
+//   * TWO accumulator buffers in TMEM (2 x BLOCK_N fp32 columns): the MMA warp fills buffer (t+1)&1 while the four
+//     epilogue warps drain buffer t&1 (tmem_full / tmem_empty mbarriers per buffer)
+//   * the TMA producer's smem ring runs continuously across tiles (no pipeline drain between tiles)
+//   * epilogue results are transposed through a per-warp shared-memory staging tile so that every global store /
+//     red.add instruction covers full 128-byte row segments (8 lanes x 16 B) instead of 32 rows x 16 B
+#pragma once
+
+namespace univl {
+
+constexpr int STAGING_ROW_BYTES = 128 + 16;                    // 128 B of payload per row + pad (bank spread)
+constexpr int STAGING_WARP_BYTES = 32 * STAGING_ROW_BYTES;     // 4608 B per epilogue warp
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmemP {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + 4 * STAGING_WARP_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct WorkItem {
+  int m0, n0, kb_begin, num_kb;
+};
+
+__device__ __forceinline__ WorkItem decode_work(int w, int m_tiles, int n_tiles, int total_kb, int kb_per, int bn) {
+  const int tiles = m_tiles * n_tiles;
+  const int split = w / tiles;
+  const int rem = w - split * tiles;
+  const int n_blk = rem / m_tiles;
+  const int m_blk = rem - n_blk * m_tiles;
+  WorkItem it;
+  it.m0 = m_blk * BLOCK_M;
+  it.n0 = n_blk * bn;
+  it.kb_begin = split * kb_per;
+  it.num_kb = min(total_kb, it.kb_begin + kb_per) - it.kb_begin;
+  return it;
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                               const GemmParams p, const int num_work) {
+  using L = GemmSmemP<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_kb = (p.Kc + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = p.k_blocks_per_split;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_N);
+        for (int i = 0; i < wi.num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          const int k_elem = (wi.kb_begin + i) * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], k_elem, wi.m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], wi.m0 + c * 64, k_elem);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[s], k_elem, wi.n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], wi.n0 + c * 64, k_elem);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      uint32_t it = 0, t = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
+        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_N);
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int i = 0; i < wi.num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const int q = warp & 3;
+    uint8_t* stage_w = smem + L::STAGING_OFFSET + q * STAGING_WARP_BYTES;
+    const int epi = p.epilogue;
+    const float alpha = p.alpha;
+    const bool out_f32 = (epi == EPI_BIAS_F32 || epi == EPI_ATOMIC_F32);
+    const int CH = out_f32 ? 32 : 64;  // columns per chunk: 128 bytes of output per row either way
+    const int rl = lane >> 3, cl = lane & 7;  // store phase: 4 rows x 8 x 16 B per instruction
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
+      const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_N);
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after_sync();
+      const int row0 = wi.m0 + q * 32;
+      const int row = row0 + lane;
+      const uint32_t t_acc = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < BLOCK_N; c += CH) {
+        const int col = wi.n0 + c;
+        if (col >= p.N) break;  // warp-uniform
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j * 16 < CH) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(t_acc + (uint32_t)(c + j * 16), r);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]) * alpha;
+          }
+        }
+        tmem_ld_wait();
+        if (p.bias != nullptr && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_F32)) {
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (e < CH && col + e < p.N) v[e] += __ldg(p.bias + col + e);
+        }
+        if (epi == EPI_GELU_BWD_BF16 || epi == EPI_ADD_BF16) {
+          if (row < p.M) {
+            const bf16* a = p.aux_in + (long long)row * p.ld_aux_in + col;
+            const bool fast = (col + 64 <= p.N) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+#pragma unroll
+            for (int e8 = 0; e8 < 8; ++e8) {
+              float x[8];
+              if (fast) {
+                const uint4 u = *reinterpret_cast<const uint4*>(a + e8 * 8);
+                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(ww[j]);
+                  x[2 * j] = f.x;
+                  x[2 * j + 1] = f.y;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = (col + e8 * 8 + j < p.N) ? __bfloat162float(a[e8 * 8 + j]) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (epi == EPI_GELU_BWD_BF16) v[e8 * 8 + j] *= gelu_erf_grad(x[j]);
+                else v[e8 * 8 + j] += x[j];
+              }
+            }
+          }
+        }
+        // ---- one or two passes through the staging tile: [pre-activation,] result ----
+        const int passes = (epi == EPI_BIAS_GELU_BF16) ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+          uint8_t* my = stage_w + lane * STAGING_ROW_BYTES;
+          if (out_f32) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4*>(my + e * 4) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          } else {
+            if (passes == 2 && pass == 1) {
+#pragma unroll
+              for (int e = 0; e < 64; ++e) v[e] = gelu_erf(v[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 64; e += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(v[e], v[e + 1]);     u.y = pack_bf16x2(v[e + 2], v[e + 3]);
+              u.z = pack_bf16x2(v[e + 4], v[e + 5]); u.w = pack_bf16x2(v[e + 6], v[e + 7]);
+              *reinterpret_cast<uint4*>(my + e * 2) = u;
+            }
+          }
+          __syncwarp();
+          // coalesced phase: instruction i covers rows 4i..4i+3, each 128 contiguous bytes
+          const int ecol = col + cl * (out_f32 ? 4 : 8);         // first element this lane stores
+          const int epl = out_f32 ? 4 : 8;                       // elements per lane
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rl;
+            const int grow = row0 + r;
+            if (grow >= p.M || ecol >= p.N) continue;
+            const uint4 u = *reinterpret_cast<const uint4*>(stage_w + r * STAGING_ROW_BYTES + cl * 16);
+            if (out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + ecol;
+              const float f0 = __uint_as_float(u.x), f1 = __uint_as_float(u.y), f2 = __uint_as_float(u.z),
+                          f3 = __uint_as_float(u.w);
+              const bool vec = (ecol + 4 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+              if (epi == EPI_ATOMIC_F32) {
+                if (vec) red_add_v4(o, f0, f1, f2, f3);
+                else {
+                  const float f[4] = {f0, f1, f2, f3};
+                  for (int j = 0; j < 4; ++j)
+                    if (ecol + j < p.N) atomicAdd(o + j, f[j]);
+                }
+              } else {
+                if (vec) *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
+                else {
+                  const float f[4] = {f0, f1, f2, f3};
+                  for (int j = 0; j < 4; ++j)
+                    if (ecol + j < p.N) o[j] = f[j];
+                }
+              }
+            } else {
+              bf16* base = (passes == 2 && pass == 0) ? p.aux_out : reinterpret_cast<bf16*>(p.out);
+              const long long ld = (passes == 2 && pass == 0) ? p.ld_aux_out : p.ldo;
+              bf16* o = base + (long long)grow * ld + ecol;
+              if ((ecol + epl <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                *reinterpret_cast<uint4*>(o) = u;
+              } else {
+                const bf16* sv = reinterpret_cast<const bf16*>(&u);
+                for (int j = 0; j < 8; ++j)
+                  if (ecol + j < p.N) o[j] = sv[j];
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace univl

@@ -19,6 +19,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace univl {
 
@@ -266,6 +267,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+}  // namespace univl
+
+#include "gemm_persistent.cuh"
+
+namespace univl {
+
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
@@ -316,6 +323,43 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p);
   UNIVL_CHECK_LAUNCH("gemm_tcgen05");
   return UNIVL_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
+                                  cudaStream_t stream) {
+  using L = GemmSmemP<BLOCK_N, STAGES>;
+  auto kern = gemm_tcgen05_persistent_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long work =
+      (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
+  if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
+  const int grid = (int)(work < sms ? work : sms);
+  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p, (int)work);
+  UNIVL_CHECK_LAUNCH("gemm_tcgen05_persistent");
+  return UNIVL_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int dispatch_major_p(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                            int splits, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, false>(ta, tb, p, splits, stream);
+  if (!a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, true>(ta, tb, p, splits, stream);
+  if (a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, true, true>(ta, tb, p, splits, stream);
+  return launch_gemm_persistent<BLOCK_N, STAGES, true, false>(ta, tb, p, splits, stream);
+}
+
+static bool use_v1_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UNIVL_GEMM_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 template <int BLOCK_N, int STAGES>
@@ -394,6 +438,11 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
   p.aux_out = reinterpret_cast<bf16*>(aux_out); p.ld_aux_out = ld_aux_out;
 
   const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
+  if (!use_v1_kernel()) {
+    if (bn == 256) return dispatch_major_p<256, 4>(amn, bmn, ta, tb, p, splits, stream);
+    if (bn == 128) return dispatch_major_p<128, 6>(amn, bmn, ta, tb, p, splits, stream);
+    return dispatch_major_p<64, 8>(amn, bmn, ta, tb, p, splits, stream);
+  }
   if (bn == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, p, splits, stream);
   if (bn == 128) return dispatch_major<128, 3>(amn, bmn, ta, tb, p, splits, stream);
   return dispatch_major<64, 4>(amn, bmn, ta, tb, p, splits, stream);

@@ -14,9 +14,10 @@
 
 namespace univl {
 
-struct AdamSeg {  // one per tensor, 32 bytes
+struct AdamSeg {  // one per CHUNK of a tensor (<= 64K elements: one CTA each), 32 bytes
   long long offset;
-  long long count;
+  int count;
+  int tensor;  // index into the per-tensor sum-of-squares array
   float lr;
   float weight_decay;
   float pad0, pad1;
@@ -35,13 +36,16 @@ __global__ void __launch_bounds__(256)
 adam_sumsq_kernel(const float* __restrict__ g, const AdamSeg* __restrict__ segs, float* __restrict__ sumsq,
                   float grad_scale) {
   __shared__ float red[8];
-  const AdamSeg s = segs[blockIdx.y];
+  const AdamSeg s = segs[blockIdx.x];
   const float* gp = g + s.offset;
   float acc = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += stride) {
-    const float x = gp[i] * grad_scale;
-    acc += x * x;
+  for (int i = threadIdx.x * 4; i < s.count; i += blockDim.x * 4) {
+    if (i + 4 <= s.count) {
+      const float4 x = *reinterpret_cast<const float4*>(gp + i);
+      acc += (x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * grad_scale * grad_scale;
+    } else {
+      for (int j = i; j < s.count; ++j) acc += gp[j] * gp[j] * grad_scale * grad_scale;
+    }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -49,7 +53,7 @@ adam_sumsq_kernel(const float* __restrict__ g, const AdamSeg* __restrict__ segs,
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    if (t != 0.f) atomicAdd(sumsq + blockIdx.y, t);
+    if (t != 0.f) atomicAdd(sumsq + s.tensor, t);
   }
 }
 
@@ -72,14 +76,14 @@ __global__ void __launch_bounds__(256)
 adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                    bf16* __restrict__ p_bf16, const AdamSeg* __restrict__ segs, const float* __restrict__ sumsq,
                    int n_tensors, const long long* __restrict__ step, AdamCfg cfg) {
-  const AdamSeg s = segs[blockIdx.y];
+  const AdamSeg s = segs[blockIdx.x];
   // a tensor whose gradient is identically zero received none this step (unused poolers etc.): the reference
   // skips parameters with `p.grad is None` entirely — no moment update, no weight decay (optimization.py:115-116)
-  if (sumsq[blockIdx.y] == 0.f) return;
+  if (sumsq[s.tensor] == 0.f) return;
   float cg = 1.f;
   if (cfg.global_clip_norm > 0.f) cg = fminf(1.f, cfg.global_clip_norm / (sqrtf(sumsq[n_tensors]) + 1e-6f));
   float ct = 1.f;
-  if (cfg.max_grad_norm > 0.f) ct = fminf(1.f, cfg.max_grad_norm / (cg * sqrtf(sumsq[blockIdx.y]) + 1e-6f));
+  if (cfg.max_grad_norm > 0.f) ct = fminf(1.f, cfg.max_grad_norm / (cg * sqrtf(sumsq[s.tensor]) + 1e-6f));
   const float gmul = cfg.grad_scale * cg * ct;
   float sched = 1.f;
   if (cfg.t_total > 0) {
@@ -87,19 +91,43 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     sched = (cfg.warmup >= 0.f && x < cfg.warmup) ? x / cfg.warmup : fmaxf((x - 1.f) / (cfg.warmup - 1.f), 0.f);
   }
   const float lr = s.lr * sched;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.count; i += stride) {
+  // chunk offsets are multiples of 64 elements: 16-byte vector accesses are aligned
+  for (int i = threadIdx.x * 4; i < s.count; i += blockDim.x * 4) {
     const long long e = s.offset + i;
-    const float gr = g[e] * gmul;
-    const float mm = cfg.b1 * m[e] + (1.f - cfg.b1) * gr;
-    const float vv = cfg.b2 * v[e] + (1.f - cfg.b2) * gr * gr;
-    float pp = p[e];
-    const float upd = mm / (sqrtf(vv) + cfg.eps) + s.weight_decay * pp;
-    pp -= lr * upd;
-    m[e] = mm;
-    v[e] = vv;
-    p[e] = pp;
-    if (p_bf16 != nullptr) p_bf16[e] = __float2bfloat16(pp);
+    if (i + 4 <= s.count) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + e);
+      float4 m4 = *reinterpret_cast<const float4*>(m + e);
+      float4 v4 = *reinterpret_cast<const float4*>(v + e);
+      float4 p4 = *reinterpret_cast<const float4*>(p + e);
+      const float gg[4] = {g4.x * gmul, g4.y * gmul, g4.z * gmul, g4.w * gmul};
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mm[j] = cfg.b1 * mm[j] + (1.f - cfg.b1) * gg[j];
+        vv[j] = cfg.b2 * vv[j] + (1.f - cfg.b2) * gg[j] * gg[j];
+        pp[j] -= lr * (mm[j] / (sqrtf(vv[j]) + cfg.eps) + s.weight_decay * pp[j]);
+      }
+      *reinterpret_cast<float4*>(m + e) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(p + e) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      if (p_bf16 != nullptr) {
+        uint2 u;
+        u.x = pack_bf16x2(pp[0], pp[1]);
+        u.y = pack_bf16x2(pp[2], pp[3]);
+        *reinterpret_cast<uint2*>(p_bf16 + e) = u;
+      }
+    } else {
+      for (int j = i; j < s.count; ++j) {
+        const long long ee = s.offset + j;
+        const float gr = g[ee] * gmul;
+        const float mm = cfg.b1 * m[ee] + (1.f - cfg.b1) * gr;
+        const float vv = cfg.b2 * v[ee] + (1.f - cfg.b2) * gr * gr;
+        float pp = p[ee];
+        pp -= lr * (mm / (sqrtf(vv) + cfg.eps) + s.weight_decay * pp);
+        m[ee] = mm; v[ee] = vv; p[ee] = pp;
+        if (p_bf16 != nullptr) p_bf16[ee] = __float2bfloat16(pp);
+      }
+    }
   }
 }
 
@@ -109,23 +137,23 @@ __global__ void adam_step_inc_kernel(long long* step) { *step += 1; }
 
 using namespace univl;
 
-// One optimizer step over flat buffers.  segs: device array of n_tensors {offset, count, lr, weight_decay, -, -};
+// One optimizer step over flat buffers.  segs: device array of n_chunks {int64 offset, int32 count, int32 tensor,
+// float lr, float weight_decay, -, -} — one CTA per chunk (chunks of <= 64K elements, offsets multiples of 64);
 // scratch: n_tensors + 1 floats; step: device int64 (incremented).  p_bf16 (same element offsets as p) may be null.
 extern "C" int univl_bert_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const void* segs,
-                                    int n_tensors, float* scratch, long long* step, float b1, float b2, float eps,
-                                    float max_grad_norm, float global_clip_norm, float warmup, long long t_total,
-                                    float grad_scale, int blocks_per_tensor, void* stream) {
+                                    int n_chunks, int n_tensors, float* scratch, long long* step, float b1, float b2,
+                                    float eps, float max_grad_norm, float global_clip_norm, float warmup,
+                                    long long t_total, float grad_scale, void* stream) {
   UNIVL_CHECK_ARG(p && g && m && v && segs && scratch && step, "bert_adam_step: null pointer");
-  UNIVL_CHECK_ARG(n_tensors > 0 && n_tensors <= 65535 && blocks_per_tensor > 0, "bert_adam_step: bad tensor count");
+  UNIVL_CHECK_ARG(n_tensors > 0 && n_chunks >= n_tensors, "bert_adam_step: bad tensor / chunk count");
   cudaStream_t st = (cudaStream_t)stream;
   AdamCfg cfg{b1, b2, eps, max_grad_norm, global_clip_norm, warmup, t_total, grad_scale};
   const AdamSeg* s = reinterpret_cast<const AdamSeg*>(segs);
   cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)(n_tensors + 1) * sizeof(float), st);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "bert_adam_step memset: %s", cudaGetErrorString(e));
-  adam_sumsq_kernel<<<dim3(blocks_per_tensor, n_tensors), 256, 0, st>>>(g, s, scratch, grad_scale);
+  adam_sumsq_kernel<<<n_chunks, 256, 0, st>>>(g, s, scratch, grad_scale);
   adam_total_kernel<<<1, 256, 0, st>>>(scratch, n_tensors);
-  adam_update_kernel<<<dim3(blocks_per_tensor, n_tensors), 256, 0, st>>>(p, g, m, v, (bf16*)p_bf16, s, scratch,
-                                                                         n_tensors, step, cfg);
+  adam_update_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, (bf16*)p_bf16, s, scratch, n_tensors, step, cfg);
   adam_step_inc_kernel<<<1, 1, 0, st>>>(step);
   UNIVL_CHECK_LAUNCH("bert_adam_step");
   return UNIVL_OK;

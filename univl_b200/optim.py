@@ -174,8 +174,13 @@ class FusedBertAdam(torch.optim.Optimizer):
                 off, n, _ = lookup[id(p)]
                 rows.append((off, n, float(grp["lr"]), float(grp["weight_decay"])))
         import struct
-        blob = b"".join(struct.pack("<qqffff", off, n, lr, wd, 0.0, 0.0) for off, n, lr, wd in rows)
-        self.segs = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        chunk = 65536
+        parts = []
+        for t, (off, n, lr, wd) in enumerate(rows):
+            for c0 in range(0, n, chunk):
+                parts.append(struct.pack("<qiiffff", off + c0, min(chunk, n - c0), t, lr, wd, 0.0, 0.0))
+        self.segs = torch.frombuffer(bytearray(b"".join(parts)), dtype=torch.uint8).to(dev)
+        self.n_chunks = len(parts)
         self.n_tensors = len(rows)
         self.scratch = torch.zeros(self.n_tensors + 1, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -211,10 +216,10 @@ class FusedBertAdam(torch.optim.Optimizer):
             self._gather_grads()
         g0 = self.param_groups[0]
         call("univl_bert_adam_step", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-             None if self.shadow is None else self.shadow.data_ptr(), self.segs.data_ptr(), self.n_tensors,
-             self.scratch.data_ptr(), self.step_dev.data_ptr(), float(g0["b1"]), float(g0["b2"]), float(g0["e"]),
-             float(g0["max_grad_norm"]), self.global_clip_norm, float(g0["warmup"]), int(g0["t_total"]),
-             self.grad_scale, 8)
+             None if self.shadow is None else self.shadow.data_ptr(), self.segs.data_ptr(), self.n_chunks,
+             self.n_tensors, self.scratch.data_ptr(), self.step_dev.data_ptr(), float(g0["b1"]), float(g0["b2"]),
+             float(g0["e"]), float(g0["max_grad_norm"]), self.global_clip_norm, float(g0["warmup"]),
+             int(g0["t_total"]), self.grad_scale)
         if self.flat is not None:
             self.flat.arena.fresh = True
         return loss

@@ -109,7 +109,7 @@ class WeightArena:
                 raise RuntimeError("univl_b200: parameters moved off %s; call model.to(device) before use" % device)
             if p.dtype != torch.float32:
                 raise RuntimeError("univl_b200: parameters must stay fp32 (got %s)" % p.dtype)
-        if not self.fresh:
+        if not self.fresh and self.entries:
             self._sync_table()
             call("univl_multi_cast_f32_to_bf16", self.table.data_ptr(), len(self.entries), 16)
         self.fresh = False
