@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--profile_steps", type=int, default=2)
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (falls back to eager "
+                    "launches if capture fails), 0: eager")
     return ap.parse_args()
 
 
@@ -204,6 +206,44 @@ def main():
         step(dev_batch)
     barrier()
 
+    # ---- optional: capture the whole step (zero-grad, fwd, bwd, all-reduce, optimizer) into one CUDA graph.  Inputs
+    # live in static device buffers; dropout masks still change every replay (device-side RNG epoch). ----
+    eager_step = step
+    launches_per_step = None
+    graphed = False
+    if a.graph:
+        try:
+            n0 = rt.launch_count()
+            static_batch = {k: v.clone() for k, v in dev_batch.items()}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eager_step(static_batch)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = rt.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = eager_step(static_batch)
+            launches_per_step = rt.launch_count() - n0
+            torch.cuda.synchronize()
+
+            def step(batch):
+                if batch is not static_batch:
+                    for k, v in batch.items():
+                        static_batch[k].copy_(v, non_blocking=True)
+                graph.replay()
+                return static_loss
+            for _ in range(2):
+                step(static_batch)
+            barrier()
+            graphed = True
+            dev_batch = static_batch
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write("bench.py: CUDA graph capture failed (%r); timing eager launches instead\n" % (exc,))
+            step = eager_step
+            torch.cuda.synchronize()
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -218,19 +258,21 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / a.steps
-    launches = rt.launch_count() - launches0
+    launches = (launches_per_step * a.steps) if graphed else (rt.launch_count() - launches0)
     loss_val = float(loss.detach())
 
     # ---- timed region 2: end to end from pinned host buffers (H2D of inputs + D2H of the loss every step) ----
     e2e = None
     if not a.no_e2e:
+        def h2d():
+            # graph mode: copy straight into the graph's static input buffers; eager: fresh device tensors
+            return host_batch if graphed else {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
         for _ in range(2):
-            float(step({k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}).detach())
+            float(step(h2d()).detach())
         barrier()
         e0.record()
         for _ in range(a.steps):
-            b = {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
-            float(step(b).detach())
+            float(step(h2d()).detach())
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1) / a.steps
@@ -252,7 +294,7 @@ def main():
         return r
     ops.gemm = timed_gemm
     for _ in range(a.profile_steps):
-        step(dev_batch)
+        eager_step(dev_batch)
     torch.cuda.synchronize()
     ops.gemm = orig_gemm
     gemm_ms = sum(s.elapsed_time(e) for s, e in prof["events"])
@@ -277,6 +319,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": samples, "parallelism": "dp%d" % world,
                    "dropout": a.dropout, "optimizer": "fused BertAdam + clip (in timed region)",
+                   "launch": "cuda-graph replay" if graphed else "eager",
                    "l2": "per-step working set (~6 GB of activations at FT-Align b=32) exceeds the 126 MB L2"},
         "gpu_launches": launches, "loss": loss_val,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -9,7 +9,9 @@
  *   - return 0 on success, negative on error (univl_last_error_string() describes it); never a silent fallback
  *   - activations bf16 row-major; parameters / statistics / losses fp32; ids, masks, labels int64 (as the
  *     reference dataloaders emit them)
- *   - dropout masks are Philox4x32-10(seed, stream_id, element index): regenerated in backward, never stored
+ *   - dropout masks are Philox4x32-10(seed, stream, element index), regenerated in backward, never stored;
+ *     `rng_state` points to device memory {uint64 seed, uint64 epoch} and the kernels use stream = stream_id +
+ *     (epoch << 20), so a captured CUDA graph draws fresh masks on every replay once univl_rng_advance ran
  */
 #ifndef UNIVL_B200_H_
 #define UNIVL_B200_H_
@@ -42,11 +44,11 @@ int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B,
  * drop_mode 2: y = dropout(LN(x + res))   (embeddings; head transforms use p = 0) */
 int univl_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, float* mean,
                         float* rstd, int rows, int cols, float eps, float p_drop, int drop_mode,
-                        unsigned long long seed, unsigned long long stream_id, void* stream);
+                        const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
 int univl_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* res, const float* gamma,
                         const float* mean, const float* rstd, void* dx_res, void* dx_dense, float* dgamma,
                         float* dbeta, float* dbias, int rows, int cols, float p_drop, int drop_mode,
-                        unsigned long long seed, unsigned long long stream_id, void* stream);
+                        const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
 /* NormalizeVideo (modeling.py:88-92): fp32 rows in, bf16 out; backward yields parameter gradients only */
 int univl_layernorm_f32_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                             int rows, int cols, float eps, void* stream);
@@ -57,24 +59,24 @@ int univl_layernorm_f32_bwd(const void* dy, const float* x, const float* gamma, 
  * text: word[id] + pos[s] (+ type[t]) -> LN -> dropout   (module_bert.py:132-146; module_decoder.py:309-320) */
 int univl_embed_text_fwd(const long long* ids, const long long* type_ids, const float* word, const float* pos,
                          const float* type, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                         int n_seq, int S, int H, int vocab, float eps, float p_drop, unsigned long long seed,
+                         int n_seq, int S, int H, int vocab, float eps, float p_drop, const unsigned long long* rng_state,
                          unsigned long long stream_id, void* stream);
 int univl_embed_text_bwd(const void* dy, const long long* ids, const long long* type_ids, const float* word,
                          const float* pos, const float* type, const float* gamma, const float* mean,
                          const float* rstd, float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta,
-                         int n_seq, int S, int H, int vocab, float p_drop, unsigned long long seed,
+                         int n_seq, int S, int H, int vocab, float p_drop, const unsigned long long* rng_state,
                          unsigned long long stream_id, void* stream);
 /* activation sources a[Na,Wa,H] (+ b[Nb,Fb,H]) + pos[s] (+ type[s>=Wa]) -> LN -> dropout
  * (module_visual.py:118-131; module_cross.py:123-138 with modeling.py:315-325; all_pairs=1 realises the B x B
  *  text-video pairing of modeling.py:341-375 without materialising the repeats) */
 int univl_embed_src_fwd(const void* a, const void* b, const float* pos, const float* type, const float* gamma,
                         const float* beta, void* y, float* mean, float* rstd, int Na, int Wa, int Nb, int Fb,
-                        int all_pairs, int H, float eps, float p_drop, unsigned long long seed,
+                        int all_pairs, int H, float eps, float p_drop, const unsigned long long* rng_state,
                         unsigned long long stream_id, void* stream);
 int univl_embed_src_bwd(const void* dy, const void* a, const void* b, const float* pos, const float* type,
                         const float* gamma, const float* mean, const float* rstd, void* da, void* db, float* dpos,
                         float* dtype, float* dgamma, float* dbeta, int Na, int Wa, int Nb, int Fb, int all_pairs,
-                        int H, float p_drop, unsigned long long seed, unsigned long long stream_id, void* stream);
+                        int H, float p_drop, const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
 
 /* ---- attention core (module_bert.py:176-196; module_decoder.py:225-245, mask :385-396) -------------------------
  * ctx = dropout(softmax(Q K^T * scale + mask)) V per (sequence, head), head dim 64, S <= 256.
@@ -82,12 +84,12 @@ int univl_embed_src_bwd(const void* dy, const void* a, const void* b, const floa
 int univl_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                         void* o, long long ldo, float* lse, const long long* mask_a, const long long* mask_b, int Wa,
                         int Fb, int Nb, int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale,
-                        float p_drop, unsigned long long seed, unsigned long long stream_id, void* stream);
+                        float p_drop, const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
 int univl_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                         const void* o, long long ldo, const float* lse, const void* d_o, long long lddo, void* dq,
                         long long lddq, void* dk, long long lddk, void* dv, long long lddv, const long long* mask_a,
                         const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq, int heads, int Sq,
-                        int Sk, int causal, float scale, float p_drop, unsigned long long seed,
+                        int Sk, int causal, float scale, float p_drop, const unsigned long long* rng_state,
                         unsigned long long stream_id, void* stream);
 
 /* ---- utilities ------------------------------------------------------------------------------------------------ */
@@ -96,6 +98,7 @@ int univl_cast_f32_to_bf16(const float* src, void* dst, long long n, void* strea
 int univl_multi_cast_f32_to_bf16(const unsigned long long* device_table, int n_tensors, int blocks_per_tensor,
                                  void* stream);
 int univl_fill_f32(float* p, float value, long long n, void* stream);
+int univl_rng_advance(unsigned long long* rng_state, void* stream); /* ++epoch (device side) */
 /* elementwise bf16: out = dy * gelu_erf'(pre) (head transforms, module_bert.py:308-312); tanh and its backward
  * (poolers, module_bert.py:290-296) */
 int univl_gelu_fwd_bf16(const void* x, void* out, long long n, void* stream);

@@ -22,6 +22,35 @@ import torch.nn.functional as F
 
 HEADS = 12
 
+# Optional bf16 emulation: round the output (and the incoming gradient) of every linear / LayerNorm / GELU / attention
+# context to bf16, i.e. what ANY implementation that keeps activations in bf16 does to the reference algorithm.
+# Used by the parity tests to size the error that bf16 storage alone causes on ill-conditioned gradients.
+_EMULATE = [False]
+
+
+class emulate_bf16:
+    def __enter__(self):
+        self.prev = _EMULATE[0]
+        _EMULATE[0] = True
+
+    def __exit__(self, *exc):
+        _EMULATE[0] = self.prev
+        return False
+
+
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _r(x):
+    return _RoundBF16.apply(x) if _EMULATE[0] else x
+
 
 # ---------------------------------------------------------------------------------------------------------
 # primitives
@@ -30,16 +59,19 @@ def layer_norm(x, w, b, eps=1e-12):
     """TF-style LayerNorm, eps inside the sqrt, biased variance (reference modules/until_module.py:49-53)."""
     u = x.mean(-1, keepdim=True)
     s = (x - u).pow(2).mean(-1, keepdim=True)
-    return w * ((x - u) / torch.sqrt(s + eps)) + b
+    return _r(w * ((x - u) / torch.sqrt(s + eps)) + b)
 
 
 def gelu(x):
     """erf GELU (reference modules/until_module.py:28-33)."""
-    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    return _r(x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))))
 
 
 def linear(x, sd, pfx):
-    return F.linear(x, sd[pfx + ".weight"], sd.get(pfx + ".bias"))
+    w = sd[pfx + ".weight"]
+    if _EMULATE[0]:
+        w = _RoundBF16.apply(w)
+    return _r(F.linear(x, w, sd.get(pfx + ".bias")))
 
 
 def additive_mask(mask01, dtype):
@@ -63,7 +95,7 @@ def multi_head_attention(q_in, kv_in, add_mask, sd, pfx, names=("query", "key", 
     scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d)  # scale BEFORE the mask add (:182-184)
     scores = scores + add_mask
     probs = torch.softmax(scores, dim=-1)
-    ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, Sq, Hd)
+    ctx = _r(torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, Sq, Hd))
     return ctx
 
 

@@ -12,7 +12,10 @@ def load_golden(name):
     return torch.load(os.path.join(GOLDEN_DIR, "ref_%s.pt" % name), weights_only=False)
 
 
-def run_oracle(cfg, batch, sd=None, seed=0, backward=True, dtype=torch.float32):
+def run_oracle(cfg, batch, sd=None, seed=0, backward=True, dtype=torch.float32, bf16_emulation=False):
+    if bf16_emulation:
+        with univl_oracle.emulate_bf16():
+            return run_oracle(cfg, batch, sd=sd, seed=seed, backward=backward, dtype=dtype)
     sd = sd if sd is not None else synth.make_state_dict(cfg, seed=seed)
     ties = synth.tied_keys(cfg)
     leaf = {}

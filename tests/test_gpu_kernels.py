@@ -12,6 +12,8 @@ from univl_b200 import ops  # noqa: E402
 from univl_b200 import runtime as rt  # noqa: E402
 
 DEV = "cuda"
+# device-resident dropout RNG state {seed, epoch} (the kernels' `rng_state` argument)
+RNG = torch.tensor([123, 0], dtype=torch.int64, device=DEV) if torch.cuda.is_available() else None
 
 
 def _bf(t):
@@ -108,18 +110,23 @@ def test_dropout_statistics_and_backward_mask_consistency():
     gamma, beta = torch.ones(cols, device=DEV), torch.zeros(cols, device=DEV)
     # mode 2 (dropout after LN) on a row pattern whose LN output is known: use x with two values
     x[:, ::2] = -1
-    y, mean, rstd = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=123, stream=7)
+    y, mean, rstd = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=RNG.data_ptr(), stream=7)
     kept = (y != 0).float().mean().item()
     assert abs(kept - (1 - p)) < 5e-3
     vals = y[y != 0].float().abs()
     assert (vals - 1 / (1 - p)).abs().max() < 2e-2            # inverted-dropout scaling
-    y2, _, _ = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=123, stream=7)
+    y2, _, _ = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=RNG.data_ptr(), stream=7)
     assert torch.equal(y, y2)                                  # same (seed, stream) -> same mask
-    y3, _, _ = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=123, stream=8)
+    y3, _, _ = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=RNG.data_ptr(), stream=8)
     assert not torch.equal(y, y3)                              # independent streams differ
+    from univl_b200.runtime import call
+    call("univl_rng_advance", RNG.data_ptr())                  # next epoch: same launch arguments, fresh mask
+    y4, _, _ = ops.layernorm_fwd(x, None, gamma, beta, p=p, mode=2, seed=RNG.data_ptr(), stream=7)
+    assert not torch.equal(y, y4) and abs((y4 != 0).float().mean().item() - (1 - p)) < 5e-3
+    RNG[1] -= 1
     # backward must regenerate the same mask: gradient is zero exactly where the output was dropped
     dy = torch.ones_like(x)
-    dx, _, _, dbeta, _ = ops.layernorm_bwd(dy, None, x, None, gamma, mean, rstd, p=p, mode=2, seed=123, stream=7,
+    dx, _, _, dbeta, _ = ops.layernorm_bwd(dy, None, x, None, gamma, mean, rstd, p=p, mode=2, seed=RNG.data_ptr(), stream=7,
                                            want_dbias=False)
     assert abs(float(dbeta.sum()) - float((y != 0).sum()) / (1 - p)) <= 1e-3 * rows * cols
 
@@ -190,24 +197,24 @@ def test_attention_dropout_forward_backward_consistent():
     spec = ops.MaskSpec(torch.ones(n_seq, S, dtype=torch.long, device=DEV))
     q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
     o0, _ = ops.attention_fwd(q, k, v, n_seq, S, S, spec)
-    o1, lse = ops.attention_fwd(q, k, v, n_seq, S, S, spec, p=p, seed=9, stream=3)
-    o2, _ = ops.attention_fwd(q, k, v, n_seq, S, S, spec, p=p, seed=9, stream=3)
+    o1, lse = ops.attention_fwd(q, k, v, n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=3)
+    o2, _ = ops.attention_fwd(q, k, v, n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=3)
     assert torch.equal(o1, o2) and not torch.equal(o0, o1)
     # E[dropout(P) V] = P V: averaged over many streams the output approaches the p=0 one
     acc = torch.zeros_like(o0, dtype=torch.float32)
     n = 64
     for s in range(n):
-        acc += ops.attention_fwd(q, k, v, n_seq, S, S, spec, p=p, seed=9, stream=100 + s)[0].float()
+        acc += ops.attention_fwd(q, k, v, n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=100 + s)[0].float()
     assert (acc / n - o0.float()).abs().mean() <= 3e-2
     # directional derivative check of the dropped function: <dO, O(q + e dq) - O(q)> / e ~ <dq_grad, dq>
     d_o = _bf(torch.randn(n_seq * S, H, device=DEV, generator=g))
     dqkv = torch.empty_like(qkv)
     ops.attention_bwd(q, k, v, o1, lse, d_o, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], n_seq, S, S, spec, p=p,
-                      seed=9, stream=3)
+                      seed=RNG.data_ptr(), stream=3)
     v_dir = _bf(torch.randn(n_seq * S, H, device=DEV, generator=g))
     eps = 0.25
     vp = _bf(v.float() + eps * v_dir.float())
-    op, _ = ops.attention_fwd(q, k, vp, n_seq, S, S, spec, p=p, seed=9, stream=3)
+    op, _ = ops.attention_fwd(q, k, vp, n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=3)
     lhs = ((op.float() - o1.float()) * d_o.float()).sum() / eps     # O is linear in V: exact up to bf16 rounding
     rhs = (dqkv[:, 2 * H:].float() * v_dir.float()).sum()
     assert abs(float(lhs - rhs)) <= 3e-2 * abs(float(rhs)) + 1.0

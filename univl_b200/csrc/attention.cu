@@ -18,8 +18,8 @@ namespace univl {
 
 constexpr int HD = 64;        // head dim
 constexpr int LDS = 72;       // smem row stride in elements (144 B: conflict-free ldmatrix)
-constexpr int ATT_FWD_WARPS = 4;
-constexpr int ATT_BWD_WARPS = 8;
+constexpr int ATT_FWD_WARPS = 8;   // upper bounds; the launch uses one warp per 16-row task up to these
+constexpr int ATT_BWD_WARPS = 12;
 
 struct AttnParams {
   const bf16 *q, *k, *v;
@@ -36,6 +36,7 @@ struct AttnParams {
   float drop_scale;
   int drop_on;
   uint64_t seed, stream;
+  const unsigned long long* rng;  // device {seed, epoch}, resolved at kernel entry (graph-replayable)
   // backward only
   const bf16* d_o;
   long long lddo;
@@ -141,7 +142,12 @@ __device__ __forceinline__ bool keep_one(const AttnParams& p, long long bh, int 
 // forward
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATT_FWD_WARPS * 32)
-attention_fwd_kernel(const AttnParams p) {
+attention_fwd_kernel(const AttnParams p_in) {
+  AttnParams p = p_in;
+  if (p.drop_on && p.rng != nullptr) {
+    p.seed = p.rng[0];
+    p.stream += p.rng[1] << 20;
+  }
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int Sq16 = (p.Sq + 15) & ~15, Sk16 = (p.Sk + 15) & ~15;
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
@@ -162,7 +168,7 @@ attention_fwd_kernel(const AttnParams p) {
   cp_async_wait_all();
   __syncthreads();
 
-  for (int q0 = warp * 16; q0 < Sq16; q0 += ATT_FWD_WARPS * 16) {
+  for (int q0 = warp * 16; q0 < Sq16; q0 += (int)(blockDim.x >> 5) * 16) {
     uint32_t qa[4][4];
     load_a_frags(sQ, q0, lane, qa);
     const int i0 = q0 + g, i1 = q0 + g + 8;
@@ -273,7 +279,12 @@ attention_fwd_kernel(const AttnParams p) {
 // backward
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATT_BWD_WARPS * 32)
-attention_bwd_kernel(const AttnParams p) {
+attention_bwd_kernel(const AttnParams p_in) {
+  AttnParams p = p_in;
+  if (p.drop_on && p.rng != nullptr) {
+    p.seed = p.rng[0];
+    p.stream += p.rng[1] << 20;
+  }
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int Sq16 = (p.Sq + 15) & ~15, Sk16 = (p.Sk + 15) & ~15;
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
@@ -322,7 +333,7 @@ attention_bwd_kernel(const AttnParams p) {
   __syncthreads();
 
   const int nQ = Sq16 >> 4, nK = Sk16 >> 4;
-  for (int task = warp; task < nQ + nK; task += ATT_BWD_WARPS) {
+  for (int task = warp; task < nQ + nK; task += (int)(blockDim.x >> 5)) {
     if (task < nQ) {
       // ---------------- dQ for 16 query rows ----------------
       const int q0 = task * 16;
@@ -462,7 +473,7 @@ attention_bwd_kernel(const AttnParams p) {
 static int fill_common(AttnParams& p, const void* q, long long ldq, const void* k, long long ldk, const void* v,
                        long long ldv, const long long* mask_a, const long long* mask_b, int Wa, int Fb, int Nb,
                        int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale, float p_drop,
-                       unsigned long long seed, unsigned long long stream_id) {
+                       const unsigned long long* rng_state, unsigned long long stream_id) {
   UNIVL_CHECK_ARG(q && k && v, "attention: null q/k/v");
   UNIVL_CHECK_ARG(n_seq >= 0 && heads > 0 && Sq > 0 && Sk > 0 && Sq <= 256 && Sk <= 256,
                   "attention: unsupported shape n_seq=%d heads=%d Sq=%d Sk=%d (S <= 256)", n_seq, heads, Sq, Sk);
@@ -480,7 +491,8 @@ static int fill_common(AttnParams& p, const void* q, long long ldq, const void* 
   p.drop_on = p_drop > 0.f;
   p.drop_threshold = dropout_threshold(p_drop);
   p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-  p.seed = seed; p.stream = stream_id;
+  UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "attention: dropout needs rng_state");
+  p.seed = 0; p.stream = stream_id; p.rng = rng_state;
   return UNIVL_OK;
 }
 
@@ -494,11 +506,11 @@ using namespace univl;
 extern "C" int univl_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                    long long ldv, void* o, long long ldo, float* lse, const long long* mask_a,
                                    const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq, int heads,
-                                   int Sq, int Sk, int causal, float scale, float p_drop, unsigned long long seed,
+                                   int Sq, int Sk, int causal, float scale, float p_drop, const unsigned long long* rng_state,
                                    unsigned long long stream_id, void* stream) {
   AttnParams p = {};
   if (int rc = fill_common(p, q, ldq, k, ldk, v, ldv, mask_a, mask_b, Wa, Fb, Nb, all_pairs, n_seq, heads, Sq, Sk,
-                           causal, scale, p_drop, seed, stream_id))
+                           causal, scale, p_drop, rng_state, stream_id))
     return rc;
   UNIVL_CHECK_ARG(o != nullptr && (ldo % 2) == 0, "attention_fwd: bad output");
   if (n_seq == 0) return UNIVL_OK;
@@ -507,7 +519,8 @@ extern "C" int univl_attention_fwd(const void* q, long long ldq, const void* k, 
   const size_t smem = (size_t)(Sq16 + 2 * Sk16) * LDS * 2 + (size_t)Sk16 * 4;
   cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_fwd smem attribute: %s", cudaGetErrorString(e));
-  attention_fwd_kernel<<<n_seq * heads, ATT_FWD_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  const int fwd_warps = (Sq16 / 16) < ATT_FWD_WARPS ? (Sq16 / 16) : ATT_FWD_WARPS;
+  attention_fwd_kernel<<<n_seq * heads, fwd_warps * 32, smem, (cudaStream_t)stream>>>(p);
   UNIVL_CHECK_LAUNCH("attention_fwd");
   return UNIVL_OK;
 }
@@ -517,10 +530,11 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
                                    long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv,
                                    long long lddv, const long long* mask_a, const long long* mask_b, int Wa, int Fb,
                                    int Nb, int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale,
-                                   float p_drop, unsigned long long seed, unsigned long long stream_id, void* stream) {
+                                   float p_drop, const unsigned long long* rng_state, unsigned long long stream_id,
+                                   void* stream) {
   AttnParams p = {};
   if (int rc = fill_common(p, q, ldq, k, ldk, v, ldv, mask_a, mask_b, Wa, Fb, Nb, all_pairs, n_seq, heads, Sq, Sk,
-                           causal, scale, p_drop, seed, stream_id))
+                           causal, scale, p_drop, rng_state, stream_id))
     return rc;
   UNIVL_CHECK_ARG(o && lse && d_o && dq && dk && dv, "attention_bwd: null pointer");
   UNIVL_CHECK_ARG((ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 2) == 0 && (lddk % 2) == 0 && (lddv % 2) == 0,
@@ -534,7 +548,9 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
   const size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16) * 4;
   cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_bwd smem attribute: %s", cudaGetErrorString(e));
-  attention_bwd_kernel<<<n_seq * heads, ATT_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  const int tasks = Sq16 / 16 + Sk16 / 16;
+  const int bwd_warps = tasks < ATT_BWD_WARPS ? tasks : ATT_BWD_WARPS;
+  attention_bwd_kernel<<<n_seq * heads, bwd_warps * 32, smem, (cudaStream_t)stream>>>(p);
   UNIVL_CHECK_LAUNCH("attention_bwd");
   return UNIVL_OK;
 }

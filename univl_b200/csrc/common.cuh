@@ -65,16 +65,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// erf-GELU exactly as the reference states it: x * 0.5 * (1 + erf(x / sqrt(2)))
-// (modules/until_module.py:28-33).
+// erf-GELU as the reference states it: x * 0.5 * (1 + erf(x / sqrt(2)))  (modules/until_module.py:28-33).
+// erf is evaluated with Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, two orders below bf16 resolution) because the
+// GEMM epilogue is instruction-bound: one MUFU.RCP + one MUFU.EX2 + 7 FMAs instead of libdevice's branchy erff.  The
+// same exponential exp(-x^2/2) serves the derivative's Gaussian term.
+__device__ __forceinline__ void erf_exp_terms(float x, float& erf_abs, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752440f;            // |x| / sqrt(2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  gauss = __expf(-z * z);                                        // exp(-x^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  erf_abs = fmaf(-poly * t, gauss, 1.0f);                        // erf(|x| / sqrt(2))
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  float e, g;
+  erf_exp_terms(x, e, g);
+  return 0.5f * x * (1.0f + copysignf(e, x));
 }
 // d/dx gelu_erf(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e, g;
+  erf_exp_terms(x, e, g);
+  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + copysignf(e, x)));
 }
 
 // ----------------------------------------------------------------------------

@@ -23,7 +23,15 @@ struct EmbDrop {
   float scale;
   uint64_t seed, stream;
   int on;
+  const unsigned long long* rng;  // device {seed, epoch}, resolved at kernel entry (graph-replayable)
 };
+__device__ __forceinline__ EmbDrop resolve_emb_drop(EmbDrop d) {
+  if (d.on && d.rng != nullptr) {
+    d.seed = d.rng[0];
+    d.stream += d.rng[1] << 20;
+  }
+  return d;
+}
 
 __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
@@ -155,7 +163,8 @@ embed_text_fwd_kernel(const long long* __restrict__ ids, const long long* __rest
                       const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
                       const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y,
                       float* __restrict__ mean_out, float* __restrict__ rstd_out, int n_seq, int S, int vocab,
-                      float eps, EmbDrop drop) {
+                      float eps, EmbDrop drop_in) {
+  const EmbDrop drop = resolve_emb_drop(drop_in);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rows = (long long)n_seq * S;
   for (long long row = (long long)blockIdx.x * EMB_WARPS + warp; row < rows; row += (long long)gridDim.x * EMB_WARPS) {
@@ -189,7 +198,8 @@ embed_text_bwd_kernel(const bf16* __restrict__ dy, const long long* __restrict__
                       const float* __restrict__ pos, const float* __restrict__ type, const float* __restrict__ gamma,
                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dword,
                       float* __restrict__ dpos, float* __restrict__ dtype, float* __restrict__ dgamma,
-                      float* __restrict__ dbeta, int n_seq, int S, int vocab, EmbDrop drop) {
+                      float* __restrict__ dbeta, int n_seq, int S, int vocab, EmbDrop drop_in) {
+  const EmbDrop drop = resolve_emb_drop(drop_in);
   __shared__ float red[EMB_WARPS][257];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rows = (long long)n_seq * S;
@@ -255,7 +265,8 @@ __global__ void __launch_bounds__(EMB_WARPS * 32)
 embed_src_fwd_kernel(SrcCfg src, const float* __restrict__ pos, const float* __restrict__ type,
                      const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long n_seq, float eps,
-                     EmbDrop drop) {
+                     EmbDrop drop_in) {
+  const EmbDrop drop = resolve_emb_drop(drop_in);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = src.Wa + src.Fb;
   const long long rows = n_seq * S;
@@ -291,7 +302,8 @@ embed_src_bwd_kernel(const bf16* __restrict__ dy, SrcCfg src, const float* __res
                      const float* __restrict__ type, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ da,
                      bf16* __restrict__ db, float* __restrict__ dpos, float* __restrict__ dtype,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, EmbDrop drop) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, EmbDrop drop_in) {
+  const EmbDrop drop = resolve_emb_drop(drop_in);
   __shared__ float red[EMB_WARPS][257];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = src.Wa + src.Fb;
@@ -354,13 +366,14 @@ embed_src_bwd_kernel(const bf16* __restrict__ dy, SrcCfg src, const float* __res
   flush_colsums(acc_b, dbeta, red, warp, lane);
 }
 
-static EmbDrop make_emb_drop(float p, unsigned long long seed, unsigned long long stream) {
+static EmbDrop make_emb_drop(float p, const unsigned long long* rng, unsigned long long stream) {
   EmbDrop d;
   d.on = p > 0.f;
   d.threshold = dropout_threshold(p);
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-  d.seed = seed;
+  d.seed = 0;
   d.stream = stream;
+  d.rng = rng;
   return d;
 }
 static int emb_grid(long long rows) {
@@ -376,7 +389,7 @@ using namespace univl;
 extern "C" int univl_embed_text_fwd(const long long* ids, const long long* type_ids, const float* word,
                                     const float* pos, const float* type, const float* gamma, const float* beta,
                                     void* y, float* mean, float* rstd, int n_seq, int S, int H, int vocab, float eps,
-                                    float p_drop, unsigned long long seed, unsigned long long stream_id,
+                                    float p_drop, const unsigned long long* rng_state, unsigned long long stream_id,
                                     void* stream) {
   UNIVL_CHECK_ARG(H == EMB_H, "embed_text_fwd: hidden size must be %d (got %d)", EMB_H, H);
   UNIVL_CHECK_ARG(ids && word && pos && gamma && beta && y && mean && rstd, "embed_text_fwd: null pointer");
@@ -384,7 +397,7 @@ extern "C" int univl_embed_text_fwd(const long long* ids, const long long* type_
   if (n_seq == 0) return UNIVL_OK;
   embed_text_fwd_kernel<<<emb_grid((long long)n_seq * S), EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
       ids, type_ids, word, pos, type, gamma, beta, (bf16*)y, mean, rstd, n_seq, S, vocab, eps,
-      make_emb_drop(p_drop, seed, stream_id));
+      make_emb_drop(p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("embed_text_fwd");
   return UNIVL_OK;
 }
@@ -393,14 +406,14 @@ extern "C" int univl_embed_text_bwd(const void* dy, const long long* ids, const 
                                     const float* word, const float* pos, const float* type, const float* gamma,
                                     const float* mean, const float* rstd, float* dword, float* dpos, float* dtype,
                                     float* dgamma, float* dbeta, int n_seq, int S, int H, int vocab, float p_drop,
-                                    unsigned long long seed, unsigned long long stream_id, void* stream) {
+                                    const unsigned long long* rng_state, unsigned long long stream_id, void* stream) {
   UNIVL_CHECK_ARG(H == EMB_H, "embed_text_bwd: hidden size must be %d (got %d)", EMB_H, H);
   UNIVL_CHECK_ARG(dy && ids && word && pos && gamma && mean && rstd && dword && dpos && dgamma && dbeta,
                   "embed_text_bwd: null pointer");
   if (n_seq == 0) return UNIVL_OK;
   embed_text_bwd_kernel<<<emb_grid((long long)n_seq * S), EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, ids, type_ids, word, pos, type, gamma, mean, rstd, dword, dpos, dtype, dgamma, dbeta, n_seq, S,
-      vocab, make_emb_drop(p_drop, seed, stream_id));
+      vocab, make_emb_drop(p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("embed_text_bwd");
   return UNIVL_OK;
 }
@@ -408,7 +421,7 @@ extern "C" int univl_embed_text_bwd(const void* dy, const long long* ids, const 
 extern "C" int univl_embed_src_fwd(const void* a, const void* b, const float* pos, const float* type,
                                    const float* gamma, const float* beta, void* y, float* mean, float* rstd, int Na,
                                    int Wa, int Nb, int Fb, int all_pairs, int H, float eps, float p_drop,
-                                   unsigned long long seed, unsigned long long stream_id, void* stream) {
+                                   const unsigned long long* rng_state, unsigned long long stream_id, void* stream) {
   UNIVL_CHECK_ARG(H == EMB_H, "embed_src_fwd: hidden size must be %d (got %d)", EMB_H, H);
   UNIVL_CHECK_ARG(a && pos && gamma && beta && y && mean && rstd, "embed_src_fwd: null pointer");
   UNIVL_CHECK_ARG(Na >= 0 && Wa > 0 && Fb >= 0 && (Fb == 0 || (b != nullptr && Nb > 0)), "embed_src_fwd: bad shape");
@@ -417,7 +430,7 @@ extern "C" int univl_embed_src_fwd(const void* a, const void* b, const float* po
   const long long n_seq = src.all_pairs ? (long long)Na * Nb : Na;
   if (n_seq == 0) return UNIVL_OK;
   embed_src_fwd_kernel<<<emb_grid(n_seq * (Wa + Fb)), EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      src, pos, type, gamma, beta, (bf16*)y, mean, rstd, n_seq, eps, make_emb_drop(p_drop, seed, stream_id));
+      src, pos, type, gamma, beta, (bf16*)y, mean, rstd, n_seq, eps, make_emb_drop(p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("embed_src_fwd");
   return UNIVL_OK;
 }
@@ -425,7 +438,7 @@ extern "C" int univl_embed_src_fwd(const void* a, const void* b, const float* po
 extern "C" int univl_embed_src_bwd(const void* dy, const void* a, const void* b, const float* pos, const float* type,
                                    const float* gamma, const float* mean, const float* rstd, void* da, void* db,
                                    float* dpos, float* dtype, float* dgamma, float* dbeta, int Na, int Wa, int Nb,
-                                   int Fb, int all_pairs, int H, float p_drop, unsigned long long seed,
+                                   int Fb, int all_pairs, int H, float p_drop, const unsigned long long* rng_state,
                                    unsigned long long stream_id, void* stream) {
   UNIVL_CHECK_ARG(H == EMB_H, "embed_src_bwd: hidden size must be %d (got %d)", EMB_H, H);
   UNIVL_CHECK_ARG(dy && a && pos && gamma && mean && rstd && dpos && dgamma && dbeta, "embed_src_bwd: null pointer");
@@ -436,7 +449,7 @@ extern "C" int univl_embed_src_bwd(const void* dy, const void* a, const void* b,
   dim3 grid(emb_grid(rows_a > rows_b ? rows_a : rows_b), Fb == 0 ? 1 : 2);
   embed_src_bwd_kernel<<<grid, EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, src, pos, type, gamma, mean, rstd, (bf16*)da, (bf16*)db, dpos, dtype, dgamma, dbeta,
-      make_emb_drop(p_drop, seed, stream_id));
+      make_emb_drop(p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("embed_src_bwd");
   return UNIVL_OK;
 }

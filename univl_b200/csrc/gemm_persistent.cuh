@@ -12,8 +12,10 @@
 
 namespace univl {
 
-constexpr int STAGING_ROW_BYTES = 128 + 16;                    // 128 B of payload per row + pad (bank spread)
-constexpr int STAGING_WARP_BYTES = 32 * STAGING_ROW_BYTES;     // 4608 B per epilogue warp
+constexpr int EPI_WARPS = 8;                                   // two warps per TMEM lane quarter, alternating chunks
+constexpr int GEMM_P_THREADS = 64 + EPI_WARPS * 32;            // TMA warp + MMA warp + epilogue warps
+constexpr int STAGING_ROW_BYTES = 128;                         // 128 B of payload per row, 16-B chunks XOR-swizzled
+constexpr int STAGING_WARP_BYTES = 32 * STAGING_ROW_BYTES;     // 4096 B per epilogue warp
 
 template <int BLOCK_N, int STAGES>
 struct GemmSmemP {
@@ -21,7 +23,7 @@ struct GemmSmemP {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGING_OFFSET + 4 * STAGING_WARP_BYTES;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + EPI_WARPS * STAGING_WARP_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
@@ -49,8 +51,115 @@ __device__ __forceinline__ WorkItem decode_work(int w, int m_tiles, int n_tiles,
   return it;
 }
 
+// One chunk (64 bf16 / 32 fp32 columns) of one warp's 32 accumulator rows: fused epilogue math on the registers `v`,
+// then a transpose through the warp's swizzled staging tile so global stores / reductions cover 128-byte row segments.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int epi, const bool out_f32, const int CH,
+                                               float (&v)[64], const int row0, const int row, const int col,
+                                               const int lane, const int rl, const int cl, uint8_t* stage_w) {
+  if (p.bias != nullptr && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_F32)) {
+#pragma unroll
+    for (int e = 0; e < 64; ++e)
+      if (e < CH && col + e < p.N) v[e] += __ldg(p.bias + col + e);
+  }
+  if (epi == EPI_GELU_BWD_BF16 || epi == EPI_ADD_BF16) {
+    if (row < p.M) {
+      const bf16* a = p.aux_in + (long long)row * p.ld_aux_in + col;
+      const bool fast = (col + 64 <= p.N) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+#pragma unroll
+      for (int e8 = 0; e8 < 8; ++e8) {
+        float x[8];
+        if (fast) {
+          const uint4 u = *reinterpret_cast<const uint4*>(a + e8 * 8);
+          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(ww[j]);
+            x[2 * j] = f.x;
+            x[2 * j + 1] = f.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (col + e8 * 8 + j < p.N) ? __bfloat162float(a[e8 * 8 + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (epi == EPI_GELU_BWD_BF16) v[e8 * 8 + j] *= gelu_erf_grad(x[j]);
+          else v[e8 * 8 + j] += x[j];
+        }
+      }
+    }
+  }
+  // ---- one or two passes through the staging tile: [pre-activation,] result ----
+  const int passes = (epi == EPI_BIAS_GELU_BF16) ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    uint8_t* my = stage_w + lane * STAGING_ROW_BYTES;
+    const int sw = lane & 7;  // 16-byte chunk j of row r lives at chunk position j ^ (r & 7): conflict-free
+    if (out_f32) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(my + (((e >> 2) ^ sw) << 4)) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+    } else {
+      if (passes == 2 && pass == 1) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e) v[e] = gelu_erf(v[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 64; e += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v[e], v[e + 1]);     u.y = pack_bf16x2(v[e + 2], v[e + 3]);
+        u.z = pack_bf16x2(v[e + 4], v[e + 5]); u.w = pack_bf16x2(v[e + 6], v[e + 7]);
+        *reinterpret_cast<uint4*>(my + (((e >> 3) ^ sw) << 4)) = u;
+      }
+    }
+    __syncwarp();
+    // coalesced phase: instruction i covers rows 4i..4i+3, each 128 contiguous bytes
+    const int ecol = col + cl * (out_f32 ? 4 : 8);         // first element this lane stores
+    const int epl = out_f32 ? 4 : 8;                       // elements per lane
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + rl;
+      const int grow = row0 + r;
+      if (grow >= p.M || ecol >= p.N) continue;
+      const uint4 u = *reinterpret_cast<const uint4*>(stage_w + r * STAGING_ROW_BYTES + ((cl ^ (r & 7)) << 4));
+      if (out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + ecol;
+        const float f0 = __uint_as_float(u.x), f1 = __uint_as_float(u.y), f2 = __uint_as_float(u.z),
+                    f3 = __uint_as_float(u.w);
+        const bool vec = (ecol + 4 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+        if (epi == EPI_ATOMIC_F32) {
+          if (vec) red_add_v4(o, f0, f1, f2, f3);
+          else {
+            const float f[4] = {f0, f1, f2, f3};
+            for (int j = 0; j < 4; ++j)
+              if (ecol + j < p.N) atomicAdd(o + j, f[j]);
+          }
+        } else {
+          if (vec) *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
+          else {
+            const float f[4] = {f0, f1, f2, f3};
+            for (int j = 0; j < 4; ++j)
+              if (ecol + j < p.N) o[j] = f[j];
+          }
+        }
+      } else {
+        bf16* base = (passes == 2 && pass == 0) ? p.aux_out : reinterpret_cast<bf16*>(p.out);
+        const long long ld = (passes == 2 && pass == 0) ? p.ld_aux_out : p.ldo;
+        bf16* o = base + (long long)grow * ld + ecol;
+        if ((ecol + epl <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+          *reinterpret_cast<uint4*>(o) = u;
+        } else {
+          const bf16* sv = reinterpret_cast<const bf16*>(&u);
+          for (int j = 0; j < 8; ++j)
+            if (ecol + j < p.N) o[j] = sv[j];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_P_THREADS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                const GemmParams p, const int num_work) {
   using L = GemmSmemP<BLOCK_N, STAGES>;
@@ -79,7 +188,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -153,8 +262,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;
-    uint8_t* stage_w = smem + L::STAGING_OFFSET + q * STAGING_WARP_BYTES;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: even / odd column chunks
+    uint8_t* stage_w = smem + L::STAGING_OFFSET + (warp - 2) * STAGING_WARP_BYTES;
     const int epi = p.epilogue;
     const float alpha = p.alpha;
     const bool out_f32 = (epi == EPI_BIAS_F32 || epi == EPI_ATOMIC_F32);
@@ -169,7 +279,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       const int row0 = wi.m0 + q * 32;
       const int row = row0 + lane;
       const uint32_t t_acc = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < BLOCK_N; c += CH) {
+      for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
         const int col = wi.n0 + c;
         if (col >= p.N) break;  // warp-uniform
         float v[64];
@@ -183,105 +293,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
           }
         }
         tmem_ld_wait();
-        if (p.bias != nullptr && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_F32)) {
-#pragma unroll
-          for (int e = 0; e < 64; ++e)
-            if (e < CH && col + e < p.N) v[e] += __ldg(p.bias + col + e);
-        }
-        if (epi == EPI_GELU_BWD_BF16 || epi == EPI_ADD_BF16) {
-          if (row < p.M) {
-            const bf16* a = p.aux_in + (long long)row * p.ld_aux_in + col;
-            const bool fast = (col + 64 <= p.N) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
-#pragma unroll
-            for (int e8 = 0; e8 < 8; ++e8) {
-              float x[8];
-              if (fast) {
-                const uint4 u = *reinterpret_cast<const uint4*>(a + e8 * 8);
-                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = unpack_bf16x2(ww[j]);
-                  x[2 * j] = f.x;
-                  x[2 * j + 1] = f.y;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = (col + e8 * 8 + j < p.N) ? __bfloat162float(a[e8 * 8 + j]) : 0.f;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (epi == EPI_GELU_BWD_BF16) v[e8 * 8 + j] *= gelu_erf_grad(x[j]);
-                else v[e8 * 8 + j] += x[j];
-              }
-            }
-          }
-        }
-        // ---- one or two passes through the staging tile: [pre-activation,] result ----
-        const int passes = (epi == EPI_BIAS_GELU_BF16) ? 2 : 1;
-        for (int pass = 0; pass < passes; ++pass) {
-          uint8_t* my = stage_w + lane * STAGING_ROW_BYTES;
-          if (out_f32) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-              *reinterpret_cast<float4*>(my + e * 4) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          } else {
-            if (passes == 2 && pass == 1) {
-#pragma unroll
-              for (int e = 0; e < 64; ++e) v[e] = gelu_erf(v[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 64; e += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(v[e], v[e + 1]);     u.y = pack_bf16x2(v[e + 2], v[e + 3]);
-              u.z = pack_bf16x2(v[e + 4], v[e + 5]); u.w = pack_bf16x2(v[e + 6], v[e + 7]);
-              *reinterpret_cast<uint4*>(my + e * 2) = u;
-            }
-          }
-          __syncwarp();
-          // coalesced phase: instruction i covers rows 4i..4i+3, each 128 contiguous bytes
-          const int ecol = col + cl * (out_f32 ? 4 : 8);         // first element this lane stores
-          const int epl = out_f32 ? 4 : 8;                       // elements per lane
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rl;
-            const int grow = row0 + r;
-            if (grow >= p.M || ecol >= p.N) continue;
-            const uint4 u = *reinterpret_cast<const uint4*>(stage_w + r * STAGING_ROW_BYTES + cl * 16);
-            if (out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + ecol;
-              const float f0 = __uint_as_float(u.x), f1 = __uint_as_float(u.y), f2 = __uint_as_float(u.z),
-                          f3 = __uint_as_float(u.w);
-              const bool vec = (ecol + 4 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-              if (epi == EPI_ATOMIC_F32) {
-                if (vec) red_add_v4(o, f0, f1, f2, f3);
-                else {
-                  const float f[4] = {f0, f1, f2, f3};
-                  for (int j = 0; j < 4; ++j)
-                    if (ecol + j < p.N) atomicAdd(o + j, f[j]);
-                }
-              } else {
-                if (vec) *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
-                else {
-                  const float f[4] = {f0, f1, f2, f3};
-                  for (int j = 0; j < 4; ++j)
-                    if (ecol + j < p.N) o[j] = f[j];
-                }
-              }
-            } else {
-              bf16* base = (passes == 2 && pass == 0) ? p.aux_out : reinterpret_cast<bf16*>(p.out);
-              const long long ld = (passes == 2 && pass == 0) ? p.ld_aux_out : p.ldo;
-              bf16* o = base + (long long)grow * ld + ecol;
-              if ((ecol + epl <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                *reinterpret_cast<uint4*>(o) = u;
-              } else {
-                const bf16* sv = reinterpret_cast<const bf16*>(&u);
-                for (int j = 0; j < 8; ++j)
-                  if (ecol + j < p.N) o[j] = sv[j];
-              }
-            }
-          }
-          __syncwarp();
-        }
+        epilogue_chunk(p, epi, out_f32, CH, v, row0, row, col, lane, rl, cl, stage_w);
       }
       // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
       tc_fence_before_sync();
@@ -295,6 +307,254 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ================================================================================================================
+// CTA-pair variant: tcgen05.mma.cta_group::2, one 256 x BLOCK_N output tile per pair of SMs.
+//
+// On the K = 768 shapes of this model the 1-CTA kernel is bound by L2 -> SM operand traffic (each 128 x 256 tile
+// re-reads a full 256-row B tile).  With cta_group::2 the two CTAs of a cluster each load their own 128 rows of A and
+// only HALF of the B tile; the tensor core reads both halves across the pair, so operand bytes per FLOP drop by a
+// third.  Layout of one UMMA (M = 256, N = BLOCK_N, K = 16): accumulator rows 0..127 live in CTA 0's TMEM, rows
+// 128..255 in CTA 1's; CTA r supplies A rows [128 r, 128 r + 128) and B rows (N index) [BLOCK_N/2 r, +BLOCK_N/2).
+// Only the leader CTA (cluster rank 0) issues MMAs; its "full" barrier collects the TMA bytes of BOTH CTAs (the
+// peer's copies signal the leader's barrier through the shared::cluster window), tcgen05.commit multicasts the
+// "slot free" / "accumulator ready" arrivals to both CTAs, and both CTAs' epilogue warps arrive on the leader's
+// "accumulator drained" barrier.
+// ================================================================================================================
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1),
+        "r"(smem_u32(leader_bar) & PEER_BIT_MASK)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem2 {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + EPI_WARPS * STAGING_WARP_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_P_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p, const int num_work) {
+  using L = GemmSmem2<BLOCK_N, STAGES>;
+  constexpr int PAIR_M = 2 * BLOCK_M;
+  constexpr int HALF_N = BLOCK_N / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (leader's copy is the live one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + PAIR_M - 1) / PAIR_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_kb = (p.Kc + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = p.k_blocks_per_split;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 2 * EPI_WARPS);  // epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  cluster_sync_all();  // barrier inits of both CTAs visible cluster-wide before any remote arrive / TMA signal
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work decode shared by all roles (tile rows are PAIR_M tall)
+  auto decode = [&](int w, int& m0, int& n0, int& kb_begin, int& num_kb) {
+    const int tiles = m_tiles * n_tiles;
+    const int split = w / tiles;
+    const int rem = w - split * tiles;
+    const int n_blk = rem / m_tiles;
+    const int m_blk = rem - n_blk * m_tiles;
+    m0 = m_blk * PAIR_M + (int)rank * BLOCK_M;  // this CTA's rows
+    n0 = n_blk * BLOCK_N;
+    kb_begin = split * kb_per;
+    num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = pair; w < num_work; w += num_pairs) {
+        int m0, n0, kb_begin, num_kb;
+        decode(w, m0, n0, kb_begin, num_kb);
+        const int nb0 = n0 + (int)rank * HALF_N;  // this CTA's half of the B tile
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
+          const int k_elem = (kb_begin + i) * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], k_elem, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d_2sm(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + c * 64, k_elem);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &tmap_b, &full_bar[s], k_elem, nb0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < HALF_N / 64; ++c)
+              tma_load_2d_2sm(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[s], nb0 + c * 64, k_elem);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N, A_MN, B_MN);
+      uint32_t it = 0, t = 0;
+      for (int w = pair; w < num_work; w += num_pairs, ++t) {
+        int m0, n0, kb_begin, num_kb;
+        decode(w, m0, n0, kb_begin, num_kb);
+        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[s]);
+        }
+        umma_commit_2sm(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own TMEM rows) ------------------------------
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stage_w = smem + L::STAGING_OFFSET + (warp - 2) * STAGING_WARP_BYTES;
+    const int epi = p.epilogue;
+    const float alpha = p.alpha;
+    const bool out_f32 = (epi == EPI_BIAS_F32 || epi == EPI_ATOMIC_F32);
+    const int CH = out_f32 ? 32 : 64;
+    const int rl = lane >> 3, cl = lane & 7;
+    uint32_t t = 0;
+    for (int w = pair; w < num_work; w += num_pairs, ++t) {
+      int m0, n0, kb_begin, num_kb;
+      decode(w, m0, n0, kb_begin, num_kb);
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after_sync();
+      const int row0 = m0 + q * 32;
+      const int row = row0 + lane;
+      const uint32_t t_acc = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
+        const int col = n0 + c;
+        if (col >= p.N) break;
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j * 16 < CH) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(t_acc + (uint32_t)(c + j * 16), r);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]) * alpha;
+          }
+        }
+        tmem_ld_wait();
+        epilogue_chunk(p, epi, out_f32, CH, v, row0, row, col, lane, rl, cl, stage_w);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  cluster_sync_all();  // neither CTA may free TMEM / exit while the peer still reads or signals
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 

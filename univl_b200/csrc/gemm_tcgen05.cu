@@ -339,7 +339,7 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
       (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
   const int grid = (int)(work < sms ? work : sms);
-  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p, (int)work);
+  kern<<<grid, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p, (int)work);
   UNIVL_CHECK_LAUNCH("gemm_tcgen05_persistent");
   return UNIVL_OK;
 }
@@ -351,6 +351,44 @@ static int dispatch_major_p(bool a_mn, bool b_mn, const CUtensorMap& ta, const C
   if (!a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, true>(ta, tb, p, splits, stream);
   if (a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, true, true>(ta, tb, p, splits, stream);
   return launch_gemm_persistent<BLOCK_N, STAGES, true, false>(ta, tb, p, splits, stream);
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
+                            cudaStream_t stream) {
+  using L = GemmSmem2<BLOCK_N, STAGES>;
+  auto kern = gemm_tcgen05_2cta_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long work =
+      (long long)((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
+  if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
+  const int pairs = (int)(work < sms / 2 ? work : sms / 2);
+  kern<<<2 * pairs, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p, (int)work);
+  UNIVL_CHECK_LAUNCH("gemm_tcgen05_2cta");
+  return UNIVL_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int dispatch_major_2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                            int splits, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, false, false>(ta, tb, p, splits, stream);
+  if (!a_mn && b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, false, true>(ta, tb, p, splits, stream);
+  if (a_mn && b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, true, true>(ta, tb, p, splits, stream);
+  return launch_gemm_2cta<BLOCK_N, STAGES, true, false>(ta, tb, p, splits, stream);
+}
+
+// 0 = auto (CTA pairs when the problem fills them), 1 = never, 2 = always when N >= 256
+static int pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UNIVL_GEMM_PAIR");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 static bool use_v1_kernel() {
@@ -398,7 +436,10 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
   int bn = block_n;
   if (bn == 0) {
     bn = 256;
-    while (bn > 64 && (long long)m_tiles * ((N + bn - 1) / bn) < 148) bn >>= 1;
+    // without split-K the tile count alone must fill the SMs; with the atomic epilogue split-K supplies the
+    // parallelism, so keep the widest (most smem-bandwidth-efficient) MMA shape
+    if (epilogue != EPI_ATOMIC_F32)
+      while (bn > 64 && (long long)m_tiles * ((N + bn - 1) / bn) < 148) bn >>= 1;
     if (N <= 64) bn = 64;
     else if (N <= 128 && bn > 128) bn = 128;
   }
@@ -418,12 +459,19 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
   int kb_per = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per - 1) / kb_per;  // no empty split
 
+  // CTA-pair kernel (256 x 256 tiles, half the B traffic per CTA) when the pairs can be kept busy
+  bool pair = false;
+  if (!use_v1_kernel() && bn == 256 && pair_mode() != 1) {
+    const long long pair_work = (long long)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * n_tiles * splits;
+    pair = pair_mode() == 2 || pair_work >= 60;
+  }
+
   CUtensorMap ta, tb;
   int rc;
   if (!a_mn_major) rc = make_tmap(&ta, A, M, Kc, lda, BLOCK_M);   // [M, Kc], box {64 k, 128 rows}
   else             rc = make_tmap(&ta, A, Kc, M, lda, BLOCK_K);   // [Kc, M], box {64 m, 64 k-rows}
   if (rc) return rc;
-  if (!b_mn_major) rc = make_tmap(&tb, B, N, Kc, ldb, bn);
+  if (!b_mn_major) rc = make_tmap(&tb, B, N, Kc, ldb, pair ? bn / 2 : bn);
   else             rc = make_tmap(&tb, B, Kc, N, ldb, BLOCK_K);
   if (rc) return rc;
 
@@ -438,6 +486,7 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
   p.aux_out = reinterpret_cast<bf16*>(aux_out); p.ld_aux_out = ld_aux_out;
 
   const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
+  if (pair) return dispatch_major_2<256, 6>(amn, bmn, ta, tb, p, splits, stream);
   if (!use_v1_kernel()) {
     if (bn == 256) return dispatch_major_p<256, 4>(amn, bmn, ta, tb, p, splits, stream);
     if (bn == 128) return dispatch_major_p<128, 6>(amn, bmn, ta, tb, p, splits, stream);

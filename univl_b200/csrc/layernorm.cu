@@ -46,7 +46,15 @@ struct DropCfg {
   uint32_t threshold;
   float scale;  // 1/(1-p)
   uint64_t seed, stream;
+  const unsigned long long* rng;  // device {seed, epoch}: resolved at kernel entry so launches are graph-replayable
 };
+__device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
+  if (d.mode != 0 && d.rng != nullptr) {
+    d.seed = d.rng[0];
+    d.stream += d.rng[1] << 20;
+  }
+  return d;
+}
 
 // keep flags of 8 consecutive elements starting at flat index idx0 (idx0 % 8 == 0): two Philox calls
 __device__ __forceinline__ void keep8(const DropCfg& d, uint64_t idx0, bool (&k)[8]) {
@@ -60,7 +68,8 @@ template <typename TIn>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows, int cols, float eps, DropCfg drop) {
+                     float* __restrict__ rstd_out, int rows, int cols, float eps, DropCfg drop_in) {
+  const DropCfg drop = resolve_drop(drop_in);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = cols >> 8;
   const float inv_cols = 1.0f / (float)cols;
@@ -129,101 +138,138 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, co
 //   dx_res   (bf16, may be null): dz                       — gradient w.r.t. the residual input (and x when no dropout)
 //   dx_dense (bf16, may be null): dz * keep/(1-p)          — gradient w.r.t. x under drop_mode 1
 //   dgamma, dbeta (fp32, atomically accumulated), dbias (fp32, optional) += column sums of dx_dense (or dz)
+__device__ __forceinline__ uint32_t keep8_mask(const DropCfg& d, uint64_t idx0) {
+  const uint4 r0 = philox4x32(d.seed, d.stream, idx0 >> 2);
+  const uint4 r1 = philox4x32(d.seed, d.stream, (idx0 >> 2) + 1);
+  return (r0.x < d.threshold ? 1u : 0u) | (r0.y < d.threshold ? 2u : 0u) | (r0.z < d.threshold ? 4u : 0u) |
+         (r0.w < d.threshold ? 8u : 0u) | (r1.x < d.threshold ? 16u : 0u) | (r1.y < d.threshold ? 32u : 0u) |
+         (r1.z < d.threshold ? 64u : 0u) | (r1.w < d.threshold ? 128u : 0u);
+}
+
+// one 8-wide vector of the row: z = pre-LayerNorm value, d = effective upstream gradient, keep = dropout bit mask
 template <typename TIn>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__device__ __forceinline__ void ln_bwd_load(const bf16* dy, const bf16* dy2, const TIn* x, const bf16* res,
+                                            long long off, const DropCfg& drop, float (&z)[8], float (&d)[8],
+                                            uint32_t& keep) {
+  load8(x + off, z);
+  keep = 0xffu;
+  if (drop.mode != 0) keep = keep8_mask(drop, (uint64_t)off);
+  if (drop.mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = ((keep >> j) & 1u) ? z[j] * drop.scale : 0.f;
+  }
+  if (res != nullptr) {
+    float r[8];
+    load8(res + off, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] += r[j];
+  }
+  load8(dy + off, d);
+  if (dy2 != nullptr) {
+    float d2[8];
+    load8(dy2 + off, d2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += d2[j];
+  }
+  if (drop.mode == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = ((keep >> j) & 1u) ? d[j] * drop.scale : 0.f;
+  }
+}
+
+// Two sweeps over the row instead of holding it in registers: sweep 1 accumulates the two row statistics and the
+// dgamma/dbeta partials, sweep 2 re-reads the (L1-resident) row and emits dz.  Halving the live registers doubles the
+// resident warps per SM, which is what this latency-bound kernel needs.
+constexpr int LNB_WARPS = 4;  // backward: 4-warp CTAs, <= 168 registers -> 3 CTAs (12 warps) per SM
+template <typename TIn, int NVEC>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 3)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const TIn* __restrict__ x,
                      const bf16* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, bf16* __restrict__ dx_res, bf16* __restrict__ dx_dense,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int rows,
-                     int cols, DropCfg drop) {
-  __shared__ float red[LN_WARPS][32 * 8 + 1];
+                     DropCfg drop_in) {
+  const DropCfg drop = resolve_drop(drop_in);
+  __shared__ float red[LNB_WARPS][32 * 8 + 1];
+  constexpr int cols = NVEC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nvec = cols >> 8;
   const float inv_cols = 1.0f / (float)cols;
-  float acc_g[LN_MAX_VEC][8], acc_b[LN_MAX_VEC][8], acc_x[LN_MAX_VEC][8];
+  float acc_g[NVEC][8], acc_b[NVEC][8], acc_x[NVEC][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i)
+  for (int i = 0; i < NVEC; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = acc_x[i][j] = 0.f;
 
-  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+  for (long long row = (long long)blockIdx.x * LNB_WARPS + warp; row < rows; row += (long long)gridDim.x * LNB_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[LN_MAX_VEC][8], g[LN_MAX_VEC][8];
-    bool keep[LN_MAX_VEC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
-      if (i < nvec) {
-        const int c = (i * 32 + lane) * 8;
-        float z[8], d[8], gm[8];
-        load8(x + row * cols + c, z);
-        if (drop.mode != 0) keep8(drop, (uint64_t)row * cols + c, keep[i]);
-        if (drop.mode == 1) {
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float z[8], d[8], gm[8];
+      uint32_t keep;
+      ln_bwd_load(dy, dy2, x, res, row * cols + c, drop, z, d, keep);
+      load8(gamma + c, gm);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] = keep[i][j] ? z[j] * drop.scale : 0.f;
-        }
-        if (res != nullptr) {
-          float r[8];
-          load8(res + row * cols + c, r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] += r[j];
-        }
-        load8(dy + row * cols + c, d);
-        if (dy2 != nullptr) {
-          float d2[8];
-          load8(dy2 + row * cols + c, d2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] += d2[j];
-        }
-        if (drop.mode == 2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] = keep[i][j] ? d[j] * drop.scale : 0.f;
-        }
-        load8(gamma + c, gm);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (z[j] - mean) * rstd;
-          g[i][j] = d[j] * gm[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          acc_g[i][j] += d[j] * xh[i][j];
-          acc_b[i][j] += d[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (z[j] - mean) * rstd;
+        const float g = d[j] * gm[j];
+        s1 += g;
+        s2 += g * xh;
+        acc_g[i][j] += d[j] * xh;
+        acc_b[i][j] += d[j];
       }
+    }
     s1 = warp_sum(s1) * inv_cols;
     s2 = warp_sum(s2) * inv_cols;
+    if (dx_res == nullptr && dx_dense == nullptr && dbias == nullptr) continue;  // parameter gradients only
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
-      if (i < nvec) {
-        const int c = (i * 32 + lane) * 8;
-        float dz[8], dd[8];
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float z[8], d[8], gm[8], dz[8], dd[8];
+      uint32_t keep;
+      ln_bwd_load(dy, dy2, x, res, row * cols + c, drop, z, d, keep);
+      load8(gamma + c, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          dz[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
-          dd[j] = (drop.mode == 1) ? (keep[i][j] ? dz[j] * drop.scale : 0.f) : dz[j];
-          acc_x[i][j] += dd[j];
-        }
-        if (dx_res != nullptr) store8(dx_res + row * cols + c, dz);
-        if (dx_dense != nullptr && dx_dense != dx_res) store8(dx_dense + row * cols + c, dd);
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (z[j] - mean) * rstd;
+        dz[j] = rstd * (d[j] * gm[j] - s1 - xh * s2);
+        dd[j] = (drop.mode == 1) ? (((keep >> j) & 1u) ? dz[j] * drop.scale : 0.f) : dz[j];
+        acc_x[i][j] += dd[j];
       }
+      if (dx_res != nullptr) store8(dx_res + row * cols + c, dz);
+      if (dx_dense != nullptr && dx_dense != dx_res) store8(dx_dense + row * cols + c, dd);
+    }
   }
-  // column sums: reduce the LN_WARPS partials through shared memory, one vector slot at a time
+  // column sums: reduce the LNB_WARPS partials through shared memory, one vector slot at a time
   for (int which = 0; which < 3; ++which) {
     float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
     if (dst == nullptr) continue;
-    for (int i = 0; i < nvec; ++i) {
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         red[warp][lane * 8 + j] = which == 0 ? acc_g[i][j] : which == 1 ? acc_b[i][j] : acc_x[i][j];
       __syncthreads();
-      for (int e = threadIdx.x; e < 256; e += LN_WARPS * 32) {
+      for (int e = threadIdx.x; e < 256; e += LNB_WARPS * 32) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) t += red[w][e];
+        for (int w = 0; w < LNB_WARPS; ++w) t += red[w][e];
         atomicAdd(dst + i * 256 + e, t);
       }
     }
+  }
+}
+
+template <typename TIn>
+static void launch_ln_bwd(int grid, cudaStream_t st, const bf16* dy, const bf16* dy2, const TIn* x, const bf16* res,
+                          const float* gamma, const float* mean, const float* rstd, bf16* dx_res, bf16* dx_dense,
+                          float* dgamma, float* dbeta, float* dbias, int rows, int cols, DropCfg drop) {
+  switch (cols >> 8) {
+    case 1: layernorm_bwd_kernel<TIn, 1><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 2: layernorm_bwd_kernel<TIn, 2><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 3: layernorm_bwd_kernel<TIn, 3><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    default: layernorm_bwd_kernel<TIn, 4><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
   }
 }
 
@@ -234,16 +280,22 @@ static int check_ln_shape(const char* what, int rows, int cols) {
   return UNIVL_OK;
 }
 
-static DropCfg make_drop(int mode, float p, unsigned long long seed, unsigned long long stream) {
+static DropCfg make_drop(int mode, float p, const unsigned long long* rng, unsigned long long stream) {
   DropCfg d;
   d.mode = (p > 0.f) ? mode : 0;
   d.threshold = dropout_threshold(p);
   d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
-  d.seed = seed;
+  d.seed = 0;
   d.stream = stream;
+  d.rng = rng;
   return d;
 }
 
+static int lnb_grid(int rows) {
+  long long blocks = ((long long)rows + LNB_WARPS - 1) / LNB_WARPS;
+  const long long cap = 148LL * 3 * 4;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
 static int ln_grid(int rows) {
   long long blocks = ((long long)rows + LN_WARPS - 1) / LN_WARPS;
   const long long cap = 148LL * 8;
@@ -257,15 +309,16 @@ using namespace univl;
 // y = LN(dropout(x) + res) [drop_mode 1]  or  dropout(LN(x + res)) [drop_mode 2];  x, res, y bf16; stats fp32.
 extern "C" int univl_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
                                    float* mean, float* rstd, int rows, int cols, float eps, float p_drop,
-                                   int drop_mode, unsigned long long seed, unsigned long long stream_id,
-                                   void* stream) {
+                                   int drop_mode, const unsigned long long* rng_state,
+                                   unsigned long long stream_id, void* stream) {
   if (int rc = check_ln_shape("layernorm_fwd", rows, cols)) return rc;
   UNIVL_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
+  UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "layernorm_fwd: dropout needs rng_state");
   UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && drop_mode >= 0 && drop_mode <= 2, "layernorm_fwd: bad dropout");
   if (rows == 0) return UNIVL_OK;
   layernorm_fwd_kernel<bf16><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
-      make_drop(drop_mode, p_drop, seed, stream_id));
+      make_drop(drop_mode, p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("layernorm_fwd");
   return UNIVL_OK;
 }
@@ -273,15 +326,16 @@ extern "C" int univl_layernorm_fwd(const void* x, const void* res, const float* 
 extern "C" int univl_layernorm_bwd(const void* dy, const void* dy2, const void* x, const void* res,
                                    const float* gamma, const float* mean, const float* rstd, void* dx_res,
                                    void* dx_dense, float* dgamma, float* dbeta, float* dbias, int rows, int cols,
-                                   float p_drop, int drop_mode, unsigned long long seed,
+                                   float p_drop, int drop_mode, const unsigned long long* rng_state,
                                    unsigned long long stream_id, void* stream) {
   if (int rc = check_ln_shape("layernorm_bwd", rows, cols)) return rc;
   UNIVL_CHECK_ARG(dy && x && gamma && mean && rstd, "layernorm_bwd: null pointer");
+  UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "layernorm_bwd: dropout needs rng_state");
   UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && drop_mode >= 0 && drop_mode <= 2, "layernorm_bwd: bad dropout");
   if (rows == 0) return UNIVL_OK;
-  layernorm_bwd_kernel<bf16><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (const bf16*)dy2, (const bf16*)x, (const bf16*)res, gamma, mean, rstd, (bf16*)dx_res,
-      (bf16*)dx_dense, dgamma, dbeta, dbias, rows, cols, make_drop(drop_mode, p_drop, seed, stream_id));
+  launch_ln_bwd<bf16>(lnb_grid(rows), (cudaStream_t)stream, (const bf16*)dy, (const bf16*)dy2, (const bf16*)x,
+                      (const bf16*)res, gamma, mean, rstd, (bf16*)dx_res, (bf16*)dx_dense, dgamma, dbeta, dbias, rows,
+                      cols, make_drop(drop_mode, p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("layernorm_bwd");
   return UNIVL_OK;
 }
@@ -293,7 +347,7 @@ extern "C" int univl_layernorm_f32_fwd(const float* x, const float* gamma, const
   UNIVL_CHECK_ARG(x && gamma && beta && y, "layernorm_f32_fwd: null pointer");
   if (rows == 0) return UNIVL_OK;
   layernorm_fwd_kernel<float><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps, make_drop(0, 0.f, 0, 0));
+      x, nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps, make_drop(0, 0.f, nullptr, 0));
   UNIVL_CHECK_LAUNCH("layernorm_f32_fwd");
   return UNIVL_OK;
 }
@@ -305,9 +359,8 @@ extern "C" int univl_layernorm_f32_bwd(const void* dy, const float* x, const flo
   if (int rc = check_ln_shape("layernorm_f32_bwd", rows, cols)) return rc;
   UNIVL_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta, "layernorm_f32_bwd: null pointer");
   if (rows == 0) return UNIVL_OK;
-  layernorm_bwd_kernel<float><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, nullptr, x, nullptr, gamma, mean, rstd, nullptr, nullptr, dgamma, dbeta, nullptr, rows, cols,
-      make_drop(0, 0.f, 0, 0));
+  launch_ln_bwd<float>(lnb_grid(rows), (cudaStream_t)stream, (const bf16*)dy, nullptr, x, nullptr, gamma, mean, rstd,
+                       nullptr, nullptr, dgamma, dbeta, nullptr, rows, cols, make_drop(0, 0.f, nullptr, 0));
   UNIVL_CHECK_LAUNCH("layernorm_f32_bwd");
   return UNIVL_OK;
 }

@@ -109,9 +109,18 @@ __global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, fl
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
+__global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1; }
+
 }  // namespace univl
 
 using namespace univl;
+
+extern "C" int univl_rng_advance(unsigned long long* rng_state, void* stream) {
+  UNIVL_CHECK_ARG(rng_state != nullptr, "rng_advance: null state");
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng_state);
+  UNIVL_CHECK_LAUNCH("rng_advance");
+  return UNIVL_OK;
+}
 
 extern "C" int univl_colsum_bf16(const void* x, long long ld, float* out, int rows, int cols, void* stream) {
   UNIVL_CHECK_ARG(x && out && rows >= 0 && cols > 0, "colsum: bad arguments");

@@ -52,8 +52,24 @@ class WeightArena:
         self.table = None
         self._ptrs = None
         self.fresh = False
-        self.seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        # dropout RNG: device-resident {seed, epoch}; kernels draw Philox(seed, stream_id + (epoch << 20), element).
+        # The epoch is advanced on the device at every training-mode entry, so a captured CUDA graph replays with
+        # fresh masks while stream ids (position of the dropout site inside a step) stay launch constants.
+        self.rng_state = None
         self.stream_counter = 0
+
+    @property
+    def seed(self):
+        """device pointer of the RNG state (the value the kernels' `rng_state` argument takes)"""
+        if self.rng_state is None:
+            s = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+            self.rng_state = torch.tensor([s, 0], dtype=torch.int64, device=self.device)
+        return self.rng_state.data_ptr()
+
+    def begin_step(self):
+        self.stream_counter = 0
+        if self.device is not None:
+            call("univl_rng_advance", self.seed)
 
     # ---- layout -----------------------------------------------------------------------------------------
     def _build(self, device):
@@ -159,6 +175,8 @@ class use_model:
             if prev is None or prev is not self.arena:
                 with torch.cuda.device(self.device):
                     self.arena.prepare(self.device)
+                    if prev is None and getattr(self.root, "training", False):
+                        self.arena.begin_step()
         _tls.arena = self.arena
         return self.arena
 
