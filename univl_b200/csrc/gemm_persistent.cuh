@@ -1,13 +1,18 @@
-// univl_b200 — persistent, warp-specialised tcgen05 GEMM (included by gemm_tcgen05.cu).
+// univl_b200 — persistent, warp-specialised tcgen05 GEMMs (included by gemm_tcgen05.cu).
 //
 // Same math and operand conventions as gemm_tcgen05_kernel, restructured so the tensor pipe never waits for the
 // epilogue:
-//   * grid = min(#work items, #SMs); each CTA walks work items (m-tile fastest, then n-tile, then k-split) round-robin
-//   * TWO accumulator buffers in TMEM (2 x BLOCK_N fp32 columns): the MMA warp fills buffer (t+1)&1 while the four
+//   * grid = min(#work items, #SMs); each CTA (or CTA pair) walks work items (m-tile fastest, then n-tile, then
+//     k-split) round-robin
+//   * TWO accumulator buffers in TMEM (2 x BLOCK_N fp32 columns): the MMA warp fills buffer (t+1)&1 while the eight
 //     epilogue warps drain buffer t&1 (tmem_full / tmem_empty mbarriers per buffer)
 //   * the TMA producer's smem ring runs continuously across tiles (no pipeline drain between tiles)
-//   * epilogue results are transposed through a per-warp shared-memory staging tile so that every global store /
-//     red.add instruction covers full 128-byte row segments (8 lanes x 16 B) instead of 32 rows x 16 B
+//   * epilogue: tcgen05.ld -> registers -> fused math -> swizzled shared-memory staging tile -> ONE bulk tensor store
+//     (cp.async.bulk.tensor, or cp.reduce.async.bulk.tensor .add for the split-K / gradient-accumulation epilogue)
+//     per 32-row x 128-byte box, issued by one lane and double-buffered, so the epilogue warps spend their issue slots
+//     on math instead of address arithmetic and per-row stores; the auxiliary operand of the GELU' / residual-add
+//     epilogues comes in through the same staging buffers by TMA load.  Outputs whose leading dimension is not a
+//     multiple of 16 bytes fall back to register -> staging -> coalesced st.global / red.global.
 #pragma once
 
 namespace univl {
@@ -15,106 +20,171 @@ namespace univl {
 constexpr int EPI_WARPS = 8;                                   // two warps per TMEM lane quarter, alternating chunks
 constexpr int GEMM_P_THREADS = 64 + EPI_WARPS * 32;            // TMA warp + MMA warp + epilogue warps
 constexpr int STAGING_ROW_BYTES = 128;                         // 128 B of payload per row, 16-B chunks XOR-swizzled
-constexpr int STAGING_WARP_BYTES = 32 * STAGING_ROW_BYTES;     // 4096 B per epilogue warp
+constexpr int STAGING_BUF_BYTES = 32 * STAGING_ROW_BYTES;      // 4096 B: one 32-row box (the TMA 128B-swizzle atom x4)
+constexpr int STAGING_WARP_BYTES = 2 * STAGING_BUF_BYTES;      // double-buffered per epilogue warp
 
-template <int BLOCK_N, int STAGES>
-struct GemmSmemP {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+template <int STAGE_BYTES_, int STAGES>
+struct SmemPlan {
+  static constexpr int STAGE_BYTES = STAGE_BYTES_;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;  // multiple of 1024
   static constexpr int BAR_OFFSET = STAGING_OFFSET + EPI_WARPS * STAGING_WARP_BYTES;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int DYN_BYTES = TOTAL + 1024;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], aux[EPI_WARPS], tmem slot
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4 + EPI_WARPS) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// bulk tensor store / reduce of one staging box; coordinates {inner (column), outer (row)}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the most recent N bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-struct WorkItem {
-  int m0, n0, kb_begin, num_kb;
+struct EpiState {
+  uint8_t* stage;       // this warp's two staging buffers
+  uint64_t* aux_bar;    // this warp's mbarrier for auxiliary-operand TMA loads
+  uint32_t buf;         // staging buffer to use next
+  uint32_t aux_phase;
 };
 
-__device__ __forceinline__ WorkItem decode_work(int w, int m_tiles, int n_tiles, int total_kb, int kb_per, int bn) {
-  const int tiles = m_tiles * n_tiles;
-  const int split = w / tiles;
-  const int rem = w - split * tiles;
-  const int n_blk = rem / m_tiles;
-  const int m_blk = rem - n_blk * m_tiles;
-  WorkItem it;
-  it.m0 = m_blk * BLOCK_M;
-  it.n0 = n_blk * bn;
-  it.kb_begin = split * kb_per;
-  it.num_kb = min(total_kb, it.kb_begin + kb_per) - it.kb_begin;
-  return it;
-}
-
-// One chunk (64 bf16 / 32 fp32 columns) of one warp's 32 accumulator rows: fused epilogue math on the registers `v`,
-// then a transpose through the warp's swizzled staging tile so global stores / reductions cover 128-byte row segments.
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int epi, const bool out_f32, const int CH,
-                                               float (&v)[64], const int row0, const int row, const int col,
-                                               const int lane, const int rl, const int cl, uint8_t* stage_w) {
-  if (p.bias != nullptr && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_F32)) {
+// ---- epilogue math on the 64 (bf16 modes) / 32 (fp32 modes) accumulator columns a thread holds for its row ----
+__device__ __forceinline__ void epi_bias(const GemmParams& p, int epi, int CH, float (&v)[64], int col) {
+  if (p.bias == nullptr || !(epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_F32)) return;
+  const float* b = p.bias + col;
+  if (col + CH <= p.N && (reinterpret_cast<uintptr_t>(b) & 15) == 0) {
+#pragma unroll
+    for (int e = 0; e < 64; e += 4)
+      if (e < CH) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(b + e));
+        v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+      }
+  } else {
 #pragma unroll
     for (int e = 0; e < 64; ++e)
-      if (e < CH && col + e < p.N) v[e] += __ldg(p.bias + col + e);
+      if (e < CH && col + e < p.N) v[e] += __ldg(b + e);
   }
+}
+__device__ __forceinline__ void epi_apply_aux(int epi, float (&v)[64], const uint4 (&a)[8]) {
+#pragma unroll
+  for (int e8 = 0; e8 < 8; ++e8) {
+    const uint32_t ww[4] = {a[e8].x, a[e8].y, a[e8].z, a[e8].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(ww[j]);
+      if (epi == EPI_GELU_BWD_BF16) {
+        v[e8 * 8 + 2 * j] *= gelu_erf_grad(f.x);
+        v[e8 * 8 + 2 * j + 1] *= gelu_erf_grad(f.y);
+      } else {
+        v[e8 * 8 + 2 * j] += f.x;
+        v[e8 * 8 + 2 * j + 1] += f.y;
+      }
+    }
+  }
+}
+// registers -> this lane's row of a swizzled staging buffer (16-byte chunk j of row r at position j ^ (r & 7), which is
+// both bank-conflict free and exactly the TMA 128B swizzle of a 1024-byte aligned box)
+__device__ __forceinline__ void stage_write(uint8_t* buf, int lane, bool out_f32, const float (&v)[64]) {
+  uint8_t* my = buf + lane * STAGING_ROW_BYTES;
+  const int sw = lane & 7;
+  if (out_f32) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4)
+      *reinterpret_cast<float4*>(my + (((e >> 2) ^ sw) << 4)) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 64; e += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(v[e], v[e + 1]);     u.y = pack_bf16x2(v[e + 2], v[e + 3]);
+      u.z = pack_bf16x2(v[e + 4], v[e + 5]); u.w = pack_bf16x2(v[e + 6], v[e + 7]);
+      *reinterpret_cast<uint4*>(my + (((e >> 3) ^ sw) << 4)) = u;
+    }
+  }
+}
+
+// TMA epilogue for one chunk.  `v` holds alpha * accumulator.
+__device__ __forceinline__ void epilogue_chunk_tma(const GemmParams& p, int epi, bool out_f32, int CH, float (&v)[64],
+                                                   int row0, int col, int lane, EpiState& st,
+                                                   const CUtensorMap* tm_out, const CUtensorMap* tm_aux) {
+  epi_bias(p, epi, CH, v, col);
+  const int passes = (epi == EPI_BIAS_GELU_BF16) ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    uint8_t* buf = st.stage + st.buf * STAGING_BUF_BYTES;
+    st.buf ^= 1;
+    if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer (two groups ago) has drained it
+    __syncwarp();
+    if (pass == 0 && (epi == EPI_GELU_BWD_BF16 || epi == EPI_ADD_BF16)) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(st.aux_bar, STAGING_BUF_BYTES);
+        tma_load_2d(buf, tm_aux, st.aux_bar, col, row0);  // rows / columns out of range arrive as zeros
+      }
+      mbar_wait(st.aux_bar, st.aux_phase);
+      st.aux_phase ^= 1;
+      uint4 a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        a[j] = *reinterpret_cast<const uint4*>(buf + lane * STAGING_ROW_BYTES + ((j ^ (lane & 7)) << 4));
+      __syncwarp();  // every lane has its row before the buffer is overwritten with results
+      epi_apply_aux(epi, v, a);
+    }
+    if (passes == 2 && pass == 1) {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) v[e] = gelu_erf(v[e]);
+    }
+    stage_write(buf, lane, out_f32, v);
+    fence_proxy_async_smem();  // generic-proxy writes visible to the bulk-copy engine
+    __syncwarp();
+    if (lane == 0) {
+      const CUtensorMap* tm = (passes == 2 && pass == 0) ? tm_aux : tm_out;
+      if (epi == EPI_ATOMIC_F32) tma_reduce_add_2d(tm, buf, col, row0);
+      else tma_store_2d(tm, buf, col, row0);
+      bulk_commit();
+    }
+  }
+}
+
+// Fallback epilogue (leading dimension not 16-byte aligned): coalesced stores through ONE staging buffer.
+__device__ __forceinline__ void epilogue_chunk_manual(const GemmParams& p, const int epi, const bool out_f32,
+                                                      const int CH, float (&v)[64], const int row0, const int row,
+                                                      const int col, const int lane, uint8_t* stage_w) {
+  const int rl = lane >> 3, cl = lane & 7;
+  epi_bias(p, epi, CH, v, col);
   if (epi == EPI_GELU_BWD_BF16 || epi == EPI_ADD_BF16) {
     if (row < p.M) {
       const bf16* a = p.aux_in + (long long)row * p.ld_aux_in + col;
-      const bool fast = (col + 64 <= p.N) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
 #pragma unroll
-      for (int e8 = 0; e8 < 8; ++e8) {
-        float x[8];
-        if (fast) {
-          const uint4 u = *reinterpret_cast<const uint4*>(a + e8 * 8);
-          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16x2(ww[j]);
-            x[2 * j] = f.x;
-            x[2 * j + 1] = f.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = (col + e8 * 8 + j < p.N) ? __bfloat162float(a[e8 * 8 + j]) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (epi == EPI_GELU_BWD_BF16) v[e8 * 8 + j] *= gelu_erf_grad(x[j]);
-          else v[e8 * 8 + j] += x[j];
-        }
+      for (int e = 0; e < 64; ++e) {
+        const float x = (col + e < p.N) ? __bfloat162float(a[e]) : 0.f;
+        if (epi == EPI_GELU_BWD_BF16) v[e] *= gelu_erf_grad(x);
+        else v[e] += x;
       }
     }
   }
-  // ---- one or two passes through the staging tile: [pre-activation,] result ----
   const int passes = (epi == EPI_BIAS_GELU_BF16) ? 2 : 1;
   for (int pass = 0; pass < passes; ++pass) {
-    uint8_t* my = stage_w + lane * STAGING_ROW_BYTES;
-    const int sw = lane & 7;  // 16-byte chunk j of row r lives at chunk position j ^ (r & 7): conflict-free
-    if (out_f32) {
+    if (passes == 2 && pass == 1) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<float4*>(my + (((e >> 2) ^ sw) << 4)) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-    } else {
-      if (passes == 2 && pass == 1) {
-#pragma unroll
-        for (int e = 0; e < 64; ++e) v[e] = gelu_erf(v[e]);
-      }
-#pragma unroll
-      for (int e = 0; e < 64; e += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(v[e], v[e + 1]);     u.y = pack_bf16x2(v[e + 2], v[e + 3]);
-        u.z = pack_bf16x2(v[e + 4], v[e + 5]); u.w = pack_bf16x2(v[e + 6], v[e + 7]);
-        *reinterpret_cast<uint4*>(my + (((e >> 3) ^ sw) << 4)) = u;
-      }
+      for (int e = 0; e < 64; ++e) v[e] = gelu_erf(v[e]);
     }
+    stage_write(stage_w, lane, out_f32, v);
     __syncwarp();
-    // coalesced phase: instruction i covers rows 4i..4i+3, each 128 contiguous bytes
-    const int ecol = col + cl * (out_f32 ? 4 : 8);         // first element this lane stores
-    const int epl = out_f32 ? 4 : 8;                       // elements per lane
+    const int ecol = col + cl * (out_f32 ? 4 : 8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + rl;
@@ -123,29 +193,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
       const uint4 u = *reinterpret_cast<const uint4*>(stage_w + r * STAGING_ROW_BYTES + ((cl ^ (r & 7)) << 4));
       if (out_f32) {
         float* o = reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + ecol;
-        const float f0 = __uint_as_float(u.x), f1 = __uint_as_float(u.y), f2 = __uint_as_float(u.z),
-                    f3 = __uint_as_float(u.w);
+        const float f[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
         const bool vec = (ecol + 4 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
         if (epi == EPI_ATOMIC_F32) {
-          if (vec) red_add_v4(o, f0, f1, f2, f3);
-          else {
-            const float f[4] = {f0, f1, f2, f3};
+          if (vec) red_add_v4(o, f[0], f[1], f[2], f[3]);
+          else
             for (int j = 0; j < 4; ++j)
               if (ecol + j < p.N) atomicAdd(o + j, f[j]);
-          }
         } else {
-          if (vec) *reinterpret_cast<float4*>(o) = make_float4(f0, f1, f2, f3);
-          else {
-            const float f[4] = {f0, f1, f2, f3};
+          if (vec) *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+          else
             for (int j = 0; j < 4; ++j)
               if (ecol + j < p.N) o[j] = f[j];
-          }
         }
       } else {
         bf16* base = (passes == 2 && pass == 0) ? p.aux_out : reinterpret_cast<bf16*>(p.out);
         const long long ld = (passes == 2 && pass == 0) ? p.ld_aux_out : p.ldo;
         bf16* o = base + (long long)grow * ld + ecol;
-        if ((ecol + epl <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        if ((ecol + 8 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
           *reinterpret_cast<uint4*>(o) = u;
         } else {
           const bf16* sv = reinterpret_cast<const bf16*>(&u);
@@ -158,18 +223,73 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
   }
 }
 
+// One accumulator tile (this warp's 32 rows x BLOCK_N columns, every other chunk) -> global memory.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_acc, int row0, int n0, int lane, int half,
+                                              EpiState& st, const CUtensorMap* tm_out, const CUtensorMap* tm_aux) {
+  const int epi = p.epilogue;
+  const float alpha = p.alpha;
+  const bool out_f32 = (epi == EPI_BIAS_F32 || epi == EPI_ATOMIC_F32);
+  const int CH = out_f32 ? 32 : 64;  // columns per chunk: 128 bytes of output per row either way
+  for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
+    const int col = n0 + c;
+    if (col >= p.N) break;  // warp-uniform
+    float v[64];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j * 16 < CH) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_acc + (uint32_t)(c + j * 16), r);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]) * alpha;
+      }
+    }
+    tmem_ld_wait();
+    if (p.tma_epilogue) epilogue_chunk_tma(p, epi, out_f32, CH, v, row0, col, lane, st, tm_out, tm_aux);
+    else epilogue_chunk_manual(p, epi, out_f32, CH, v, row0, row0 + lane, col, lane, st.stage);
+  }
+}
+
+struct WorkItem {
+  int m0, n0, kb_begin, num_kb;
+};
+// tile_m = rows covered by one work item (128, or 256 for a CTA pair)
+__device__ __forceinline__ WorkItem decode_work(int w, int m_tiles, int n_tiles, int total_kb, int kb_per, int tile_m,
+                                                int bn) {
+  const int tiles = m_tiles * n_tiles;
+  const int split = w / tiles;
+  const int rem = w - split * tiles;
+  const int n_blk = rem / m_tiles;
+  const int m_blk = rem - n_blk * m_tiles;
+  WorkItem it;
+  it.m0 = m_blk * tile_m;
+  it.n0 = n_blk * bn;
+  it.kb_begin = split * kb_per;
+  it.num_kb = min(total_kb, it.kb_begin + kb_per) - it.kb_begin;
+  return it;
+}
+
+// ================================================================================================================
+// 1-CTA persistent kernel
+// ================================================================================================================
+template <int BLOCK_N, int STAGES>
+using GemmSmemP = SmemPlan<BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2, STAGES>;
+
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_P_THREADS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                               const GemmParams p, const int num_work) {
+                               const __grid_constant__ CUtensorMap tmap_out,
+                               const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p, const int num_work) {
   using L = GemmSmemP<BLOCK_N, STAGES>;
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* aux_bar = tmem_empty_bar + 2;         // [EPI_WARPS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,6 +302,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_epilogue) {
+      tma_prefetch_desc(&tmap_out);
+      tma_prefetch_desc(&tmap_aux);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -190,6 +314,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], EPI_WARPS);  // one arrival per epilogue warp
     }
+    for (int e = 0; e < EPI_WARPS; ++e) mbar_init(&aux_bar[e], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -203,13 +328,13 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     if (lane == 0) {
       uint32_t it = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_N);
+        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_M, BLOCK_N);
         for (int i = 0; i < wi.num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
+          uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
           const int k_elem = (wi.kb_begin + i) * BLOCK_K;
           if (!A_MN) {
@@ -235,7 +360,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
       uint32_t it = 0, t = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
-        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_N);
+        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_M, BLOCK_N);
         const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after_sync();
@@ -246,7 +371,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BLOCK_K * 128, 1024)
@@ -264,42 +389,21 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     // ------------------------------ epilogue ----------------------------------
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: even / odd column chunks
-    uint8_t* stage_w = smem + L::STAGING_OFFSET + (warp - 2) * STAGING_WARP_BYTES;
-    const int epi = p.epilogue;
-    const float alpha = p.alpha;
-    const bool out_f32 = (epi == EPI_BIAS_F32 || epi == EPI_ATOMIC_F32);
-    const int CH = out_f32 ? 32 : 64;  // columns per chunk: 128 bytes of output per row either way
-    const int rl = lane >> 3, cl = lane & 7;  // store phase: 4 rows x 8 x 16 B per instruction
+    EpiState st{smem + L::STAGING_OFFSET + (warp - 2) * STAGING_WARP_BYTES, &aux_bar[warp - 2], 0u, 0u};
     uint32_t t = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
-      const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_N);
+      const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_M, BLOCK_N);
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
-      const int row0 = wi.m0 + q * 32;
-      const int row = row0 + lane;
-      const uint32_t t_acc = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
-        const int col = wi.n0 + c;
-        if (col >= p.N) break;  // warp-uniform
-        float v[64];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j * 16 < CH) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(t_acc + (uint32_t)(c + j * 16), r);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]) * alpha;
-          }
-        }
-        tmem_ld_wait();
-        epilogue_chunk(p, epi, out_f32, CH, v, row0, row, col, lane, rl, cl, stage_w);
-      }
+      epilogue_tile<BLOCK_N>(p, tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16), wi.m0 + q * 32, wi.n0, lane,
+                             half, st, &tmap_out, &tmap_aux);
       // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (lane == 0) bulk_wait_all();  // outstanding bulk stores still read this CTA's shared memory
   }
 
   tc_fence_before_sync();
@@ -310,19 +414,17 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
   }
 }
 
-
 // ================================================================================================================
 // CTA-pair variant: tcgen05.mma.cta_group::2, one 256 x BLOCK_N output tile per pair of SMs.
 //
-// On the K = 768 shapes of this model the 1-CTA kernel is bound by L2 -> SM operand traffic (each 128 x 256 tile
-// re-reads a full 256-row B tile).  With cta_group::2 the two CTAs of a cluster each load their own 128 rows of A and
-// only HALF of the B tile; the tensor core reads both halves across the pair, so operand bytes per FLOP drop by a
-// third.  Layout of one UMMA (M = 256, N = BLOCK_N, K = 16): accumulator rows 0..127 live in CTA 0's TMEM, rows
-// 128..255 in CTA 1's; CTA r supplies A rows [128 r, 128 r + 128) and B rows (N index) [BLOCK_N/2 r, +BLOCK_N/2).
-// Only the leader CTA (cluster rank 0) issues MMAs; its "full" barrier collects the TMA bytes of BOTH CTAs (the
-// peer's copies signal the leader's barrier through the shared::cluster window), tcgen05.commit multicasts the
-// "slot free" / "accumulator ready" arrivals to both CTAs, and both CTAs' epilogue warps arrive on the leader's
-// "accumulator drained" barrier.
+// On the K = 768 shapes of this model the 1-CTA kernel re-reads a full 256-row B tile per 128 x 256 output tile.  With
+// cta_group::2 the two CTAs of a cluster each load their own 128 rows of A and only HALF of the B tile; the tensor
+// core reads both halves across the pair, so operand bytes per FLOP drop by a third.  Layout of one UMMA (M = 256,
+// N = BLOCK_N, K = 16): accumulator rows 0..127 live in CTA 0's TMEM, rows 128..255 in CTA 1's; CTA r supplies A rows
+// [128 r, 128 r + 128) and B rows (N index) [BLOCK_N/2 r, +BLOCK_N/2).  Only the leader CTA (cluster rank 0) issues
+// MMAs; its "full" barrier collects the TMA bytes of BOTH CTAs (the peer's copies signal the leader's barrier through
+// the shared::cluster window), tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs,
+// and both CTAs' epilogue warps arrive on the leader's "accumulator drained" barrier.
 // ================================================================================================================
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
@@ -374,30 +476,25 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
 }
 
 template <int BLOCK_N, int STAGES>
-struct GemmSmem2 {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows of A
-  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half of the B tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGING_OFFSET + EPI_WARPS * STAGING_WARP_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int DYN_BYTES = TOTAL + 1024;
-};
+using GemmSmem2 = SmemPlan<BLOCK_M * BLOCK_K * 2 + (BLOCK_N / 2) * BLOCK_K * 2, STAGES>;
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_P_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                          const GemmParams p, const int num_work) {
   using L = GemmSmem2<BLOCK_N, STAGES>;
   constexpr int PAIR_M = 2 * BLOCK_M;
   constexpr int HALF_N = BLOCK_N / 2;
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (leader's copy is the live one)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2] (the leader's copy is the live one)
+  uint64_t* aux_bar = tmem_empty_bar + 2;         // [EPI_WARPS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -413,6 +510,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_epilogue) {
+      tma_prefetch_desc(&tmap_out);
+      tma_prefetch_desc(&tmap_aux);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -421,6 +522,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 2 * EPI_WARPS);  // epilogue warps of both CTAs
     }
+    for (int e = 0; e < EPI_WARPS; ++e) mbar_init(&aux_bar[e], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -429,35 +531,22 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work decode shared by all roles (tile rows are PAIR_M tall)
-  auto decode = [&](int w, int& m0, int& n0, int& kb_begin, int& num_kb) {
-    const int tiles = m_tiles * n_tiles;
-    const int split = w / tiles;
-    const int rem = w - split * tiles;
-    const int n_blk = rem / m_tiles;
-    const int m_blk = rem - n_blk * m_tiles;
-    m0 = m_blk * PAIR_M + (int)rank * BLOCK_M;  // this CTA's rows
-    n0 = n_blk * BLOCK_N;
-    kb_begin = split * kb_per;
-    num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;
-  };
-
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
     if (lane == 0) {
       uint32_t it = 0;
       for (int w = pair; w < num_work; w += num_pairs) {
-        int m0, n0, kb_begin, num_kb;
-        decode(w, m0, n0, kb_begin, num_kb);
-        const int nb0 = n0 + (int)rank * HALF_N;  // this CTA's half of the B tile
-        for (int i = 0; i < num_kb; ++i, ++it) {
+        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, PAIR_M, BLOCK_N);
+        const int m0 = wi.m0 + (int)rank * BLOCK_M;   // this CTA's rows of A
+        const int nb0 = wi.n0 + (int)rank * HALF_N;   // this CTA's half of the B tile
+        for (int i = 0; i < wi.num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
+          uint8_t* sb = sa + A_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
-          const int k_elem = (kb_begin + i) * BLOCK_K;
+          const int k_elem = (wi.kb_begin + i) * BLOCK_K;
           if (!A_MN) {
             tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], k_elem, m0);
           } else {
@@ -481,19 +570,18 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N, A_MN, B_MN);
       uint32_t it = 0, t = 0;
       for (int w = pair; w < num_work; w += num_pairs, ++t) {
-        int m0, n0, kb_begin, num_kb;
-        decode(w, m0, n0, kb_begin, num_kb);
+        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, PAIR_M, BLOCK_N);
         const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int i = 0; i < num_kb; ++i, ++it) {
+        for (int i = 0; i < wi.num_kb; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BLOCK_K * 128, 1024)
@@ -511,42 +599,20 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ------------------------------ epilogue (both CTAs, own TMEM rows) ------------------------------
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* stage_w = smem + L::STAGING_OFFSET + (warp - 2) * STAGING_WARP_BYTES;
-    const int epi = p.epilogue;
-    const float alpha = p.alpha;
-    const bool out_f32 = (epi == EPI_BIAS_F32 || epi == EPI_ATOMIC_F32);
-    const int CH = out_f32 ? 32 : 64;
-    const int rl = lane >> 3, cl = lane & 7;
+    EpiState st{smem + L::STAGING_OFFSET + (warp - 2) * STAGING_WARP_BYTES, &aux_bar[warp - 2], 0u, 0u};
     uint32_t t = 0;
     for (int w = pair; w < num_work; w += num_pairs, ++t) {
-      int m0, n0, kb_begin, num_kb;
-      decode(w, m0, n0, kb_begin, num_kb);
+      const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, PAIR_M, BLOCK_N);
       const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
-      const int row0 = m0 + q * 32;
-      const int row = row0 + lane;
-      const uint32_t t_acc = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
-        const int col = n0 + c;
-        if (col >= p.N) break;
-        float v[64];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j * 16 < CH) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(t_acc + (uint32_t)(c + j * 16), r);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]) * alpha;
-          }
-        }
-        tmem_ld_wait();
-        epilogue_chunk(p, epi, out_f32, CH, v, row0, row, col, lane, rl, cl, stage_w);
-      }
+      epilogue_tile<BLOCK_N>(p, tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16),
+                             wi.m0 + (int)rank * BLOCK_M + q * 32, wi.n0, lane, half, st, &tmap_out, &tmap_aux);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
     }
+    if (lane == 0) bulk_wait_all();
   }
 
   __syncwarp();

@@ -44,6 +44,7 @@ struct GemmParams {
   long long ld_aux_in;
   bf16* aux_out;
   long long ld_aux_out;
+  int tma_epilogue;  // persistent kernels: 1 = bulk tensor stores through tmap_out / tmap_aux, 0 = manual stores
 };
 
 constexpr int BLOCK_M = 128;
@@ -311,6 +312,24 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long
   return UNIVL_OK;
 }
 
+// tensor map of an epilogue operand: row-major [rows, cols] of bf16 or fp32, box = 32 rows x 128 bytes, 128B swizzle
+static int make_tmap_epi(CUtensorMap* tm, const void* ptr, bool f32, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(UNIVL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int esize = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(UNIVL_ERR_CUDA, "cuTensorMapEncodeTiled(epilogue) failed (%d) rows=%lld cols=%lld ld=%lld ptr=%p",
+                     (int)r, rows, cols, ld, ptr);
+  return UNIVL_OK;
+}
+
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
                        cudaStream_t stream) {
@@ -326,8 +345,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 }
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
-static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
-                                  cudaStream_t stream) {
+static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                                  const CUtensorMap& tx, const GemmParams& p, int splits, cudaStream_t stream) {
   using L = GemmSmemP<BLOCK_N, STAGES>;
   auto kern = gemm_tcgen05_persistent_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
@@ -339,23 +358,23 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
       (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
   const int grid = (int)(work < sms ? work : sms);
-  kern<<<grid, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p, (int)work);
+  kern<<<grid, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, to, tx, p, (int)work);
   UNIVL_CHECK_LAUNCH("gemm_tcgen05_persistent");
   return UNIVL_OK;
 }
 
 template <int BLOCK_N, int STAGES>
-static int dispatch_major_p(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                            int splits, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, false>(ta, tb, p, splits, stream);
-  if (!a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, true>(ta, tb, p, splits, stream);
-  if (a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, true, true>(ta, tb, p, splits, stream);
-  return launch_gemm_persistent<BLOCK_N, STAGES, true, false>(ta, tb, p, splits, stream);
+static int dispatch_major_p(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                            const CUtensorMap& tx, const GemmParams& p, int splits, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, false>(ta, tb, to, tx, p, splits, stream);
+  if (!a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, false, true>(ta, tb, to, tx, p, splits, stream);
+  if (a_mn && b_mn) return launch_gemm_persistent<BLOCK_N, STAGES, true, true>(ta, tb, to, tx, p, splits, stream);
+  return launch_gemm_persistent<BLOCK_N, STAGES, true, false>(ta, tb, to, tx, p, splits, stream);
 }
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
-static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
-                            cudaStream_t stream) {
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                            const CUtensorMap& tx, const GemmParams& p, int splits, cudaStream_t stream) {
   using L = GemmSmem2<BLOCK_N, STAGES>;
   auto kern = gemm_tcgen05_2cta_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
@@ -367,18 +386,18 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
       (long long)((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
   const int pairs = (int)(work < sms / 2 ? work : sms / 2);
-  kern<<<2 * pairs, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p, (int)work);
+  kern<<<2 * pairs, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, to, tx, p, (int)work);
   UNIVL_CHECK_LAUNCH("gemm_tcgen05_2cta");
   return UNIVL_OK;
 }
 
 template <int BLOCK_N, int STAGES>
-static int dispatch_major_2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                            int splits, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, false, false>(ta, tb, p, splits, stream);
-  if (!a_mn && b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, false, true>(ta, tb, p, splits, stream);
-  if (a_mn && b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, true, true>(ta, tb, p, splits, stream);
-  return launch_gemm_2cta<BLOCK_N, STAGES, true, false>(ta, tb, p, splits, stream);
+static int dispatch_major_2(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                            const CUtensorMap& tx, const GemmParams& p, int splits, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, false, false>(ta, tb, to, tx, p, splits, stream);
+  if (!a_mn && b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, false, true>(ta, tb, to, tx, p, splits, stream);
+  if (a_mn && b_mn) return launch_gemm_2cta<BLOCK_N, STAGES, true, true>(ta, tb, to, tx, p, splits, stream);
+  return launch_gemm_2cta<BLOCK_N, STAGES, true, false>(ta, tb, to, tx, p, splits, stream);
 }
 
 // 0 = auto (CTA pairs when the problem fills them), 1 = never, 2 = always when N >= 256
@@ -484,13 +503,40 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
   p.bias = bias;
   p.aux_in = reinterpret_cast<const bf16*>(aux_in); p.ld_aux_in = ld_aux_in;
   p.aux_out = reinterpret_cast<bf16*>(aux_out); p.ld_aux_out = ld_aux_out;
+  p.tma_epilogue = 0;
 
   const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
-  if (pair) return dispatch_major_2<256, 6>(amn, bmn, ta, tb, p, splits, stream);
   if (!use_v1_kernel()) {
-    if (bn == 256) return dispatch_major_p<256, 4>(amn, bmn, ta, tb, p, splits, stream);
-    if (bn == 128) return dispatch_major_p<128, 6>(amn, bmn, ta, tb, p, splits, stream);
-    return dispatch_major_p<64, 8>(amn, bmn, ta, tb, p, splits, stream);
+    // epilogue operands by bulk tensor copies when their layout allows it (16-byte aligned base and row pitch)
+    const bool out_f32 = epilogue == EPI_BIAS_F32 || epilogue == EPI_ATOMIC_F32;
+    const void* aux = epilogue == EPI_BIAS_GELU_BF16 ? aux_out
+                      : (epilogue == EPI_GELU_BWD_BF16 || epilogue == EPI_ADD_BF16) ? aux_in : nullptr;
+    const long long ld_aux = epilogue == EPI_BIAS_GELU_BF16 ? ld_aux_out : ld_aux_in;
+    bool tma_ok = ((uintptr_t)out & 15) == 0 && ((ldo * (out_f32 ? 4 : 2)) % 16) == 0;
+    if (aux != nullptr) tma_ok = tma_ok && ((uintptr_t)aux & 15) == 0 && ((ld_aux * 2) % 16) == 0;
+    static int force_manual = -1;
+    if (force_manual < 0) {
+      const char* e = getenv("UNIVL_GEMM_MANUAL_EPILOGUE");
+      force_manual = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (force_manual) tma_ok = false;
+    CUtensorMap to, tx;
+    if (tma_ok) {
+      if ((rc = make_tmap_epi(&to, out, out_f32, M, N, ldo))) return rc;
+      if (aux != nullptr) {
+        if ((rc = make_tmap_epi(&tx, aux, false, M, N, ld_aux))) return rc;
+      } else {
+        tx = to;
+      }
+    } else {
+      to = ta;  // valid descriptors, never dereferenced
+      tx = ta;
+    }
+    p.tma_epilogue = tma_ok ? 1 : 0;
+    if (pair) return dispatch_major_2<256, 5>(amn, bmn, ta, tb, to, tx, p, splits, stream);
+    if (bn == 256) return dispatch_major_p<256, 3>(amn, bmn, ta, tb, to, tx, p, splits, stream);
+    if (bn == 128) return dispatch_major_p<128, 5>(amn, bmn, ta, tb, to, tx, p, splits, stream);
+    return dispatch_major_p<64, 6>(amn, bmn, ta, tb, to, tx, p, splits, stream);
   }
   if (bn == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, p, splits, stream);
   if (bn == 128) return dispatch_major<128, 3>(amn, bmn, ta, tb, p, splits, stream);
