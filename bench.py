@@ -189,22 +189,33 @@ def main():
     dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batch.values())
 
-    def step(batch):
+    def fwd_bwd(batch):
         opt.zero_grad()
         loss = model(**batch)
         loss.backward()
+        return loss
+
+    def step(batch):
+        loss = fwd_bwd(batch)
         reducer.all_reduce()
         opt.step()
         return loss
+
+    def stage(msg):
+        if os.environ.get("UNIVL_BENCH_VERBOSE"):
+            sys.stderr.write("[bench rank %d] %s\n" % (rank, msg))
+            sys.stderr.flush()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    stage("model + optimizer built; warm-up")
     for _ in range(a.warmup):
         step(dev_batch)
     barrier()
+    stage("warm-up done")
 
     # ---- optional: capture the whole step (zero-grad, fwd, bwd, all-reduce, optimizer) into one CUDA graph.  Inputs
     # live in static device buffers; dropout masks still change every replay (device-side RNG epoch). ----
@@ -222,17 +233,30 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             n0 = rt.launch_count()
+            # N > 1: the NCCL all-reduce stays an eager call between two graphs (forward+backward | optimizer)
             graph = torch.cuda.CUDAGraph()
+            graph_opt = None
             with torch.cuda.graph(graph):
-                static_loss = eager_step(static_batch)
+                if world == 1:
+                    static_loss = eager_step(static_batch)
+                else:
+                    static_loss = fwd_bwd(static_batch)
+            if world > 1:
+                graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_opt):
+                    opt.step()
             launches_per_step = rt.launch_count() - n0
             torch.cuda.synchronize()
+            stage("graphs captured")
 
             def step(batch):
                 if batch is not static_batch:
                     for k, v in batch.items():
                         static_batch[k].copy_(v, non_blocking=True)
                 graph.replay()
+                if graph_opt is not None:
+                    reducer.all_reduce()
+                    graph_opt.replay()
                 return static_loss
             for _ in range(2):
                 step(static_batch)
@@ -248,6 +272,7 @@ def main():
     if sampler:
         sampler.start()
 
+    stage("timed region")
     # ---- timed region 1: inputs resident in HBM ----
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = rt.launch_count()

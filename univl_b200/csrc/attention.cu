@@ -126,16 +126,14 @@ __device__ __forceinline__ void mma_p_z(const uint32_t (&pa)[4], const bf16* Z, 
   }
 }
 
-// keep flags for (query i, keys j0, j0+1), j0 even: one Philox call
-__device__ __forceinline__ void keep_pair(const AttnParams& p, long long bh, int i, int j0, int Skq, bool& k0, bool& k1) {
-  const uint4 r = philox4x32(p.seed, p.stream, (uint64_t)((bh * p.Sq + i) * (long long)Skq + (j0 >> 2)));
-  if (j0 & 2) { k0 = r.z < p.drop_threshold; k1 = r.w < p.drop_threshold; }
-  else        { k0 = r.x < p.drop_threshold; k1 = r.y < p.drop_threshold; }
-}
-__device__ __forceinline__ bool keep_one(const AttnParams& p, long long bh, int i, int j, int Skq) {
-  const uint4 r = philox4x32(p.seed, p.stream, (uint64_t)((bh * p.Sq + i) * (long long)Skq + (j >> 2)));
-  const uint32_t w = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
-  return w < p.drop_threshold;
+// Dropout randoms are laid out to match the mma fragment: for the 16 x 16 tile (query block qb, key block kb) the
+// element (i, j) uses 16-bit word w = (j & 1) | ((i >> 3) & 1) << 1 | ((j >> 3) & 1) << 2 of
+// Philox(seed, stream, ((bh * nQb + qb) * nKb + kb) * 32 + lane_f),  lane_f = (i & 7) << 2 | (j & 7) >> 1.
+// In the query-major passes (forward, dQ) lane_f is the thread's own lane and its 8 tile elements are the 8 words of
+// ONE call; the key-major pass (dK/dV) needs two calls per tile.
+__device__ __forceinline__ uint4 tile_rng(const AttnParams& p, long long bh, int qb, int kb, int nQb, int nKb,
+                                          int lane_f) {
+  return philox4x32(p.seed, p.stream, (uint64_t)(((bh * nQb + qb) * (long long)nKb + kb) * 32 + lane_f));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -159,7 +157,6 @@ attention_fwd_kernel(const AttnParams p_in) {
   const long long bh = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int Skq = Sk16 >> 2;
 
   load_head_tile(sQ, p.q + (long long)seq * p.Sq * p.ldq + h * HD, p.ldq, p.Sq, Sq16);
   load_head_tile(sK, p.k + (long long)seq * p.Sk * p.ldk + h * HD, p.ldk, p.Sk, Sk16);
@@ -226,14 +223,11 @@ attention_fwd_kernel(const AttnParams p_in) {
     for (int j0 = 0; j0 < Sk16; j0 += 16) {
       float s[2][4];
       mma_a_yT(qa, sK, j0, lane, s);
+      uint4 rnd = make_uint4(0, 0, 0, 0);
+      if (p.drop_on) rnd = tile_rng(p, bh, q0 >> 4, j0 >> 4, Sq16 >> 4, Sk16 >> 4, lane);
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb) {
         const int jb = j0 + nb * 8 + 2 * t;
-        bool k00 = true, k01 = true, k10 = true, k11 = true;
-        if (p.drop_on) {
-          keep_pair(p, bh, i0 < p.Sq ? i0 : 0, jb, Skq, k00, k01);
-          keep_pair(p, bh, i1 < p.Sq ? i1 : 0, jb, Skq, k10, k11);
-        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = jb + e;
@@ -246,8 +240,8 @@ attention_fwd_kernel(const AttnParams p_in) {
           float p0 = __expf(s[nb][e] * p.scale + a0 - m0) * inv0;
           float p1 = __expf(s[nb][2 + e] * p.scale + a1 - m1) * inv1;
           if (p.drop_on) {
-            p0 = (e == 0 ? k00 : k01) ? p0 * p.drop_scale : 0.f;
-            p1 = (e == 0 ? k10 : k11) ? p1 * p.drop_scale : 0.f;
+            p0 = philox_u16(rnd, e | (nb << 2)) < p.drop_threshold ? p0 * p.drop_scale : 0.f;
+            p1 = philox_u16(rnd, e | 2 | (nb << 2)) < p.drop_threshold ? p1 * p.drop_scale : 0.f;
           }
           s[nb][e] = p0;
           s[nb][2 + e] = p1;
@@ -299,7 +293,6 @@ attention_bwd_kernel(const AttnParams p_in) {
   const long long bh = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int Skq = Sk16 >> 2;
 
   load_head_tile(sQ, p.q + (long long)seq * p.Sq * p.ldq + h * HD, p.ldq, p.Sq, Sq16);
   load_head_tile(sdO, p.d_o + (long long)seq * p.Sq * p.lddo + h * HD, p.lddo, p.Sq, Sq16);
@@ -351,14 +344,11 @@ attention_bwd_kernel(const AttnParams p_in) {
         float s[2][4], dp[2][4];
         mma_a_yT(qa, sK, j0, lane, s);
         mma_a_yT(da, sV, j0, lane, dp);
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (p.drop_on) rnd = tile_rng(p, bh, q0 >> 4, j0 >> 4, Sq16 >> 4, Sk16 >> 4, lane);
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
           const int jb = j0 + nb * 8 + 2 * t;
-          bool k00 = true, k01 = true, k10 = true, k11 = true;
-          if (p.drop_on) {
-            keep_pair(p, bh, i0 < p.Sq ? i0 : 0, jb, Skq, k00, k01);
-            keep_pair(p, bh, i1 < p.Sq ? i1 : 0, jb, Skq, k10, k11);
-          }
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int j = jb + e;
@@ -372,8 +362,8 @@ attention_bwd_kernel(const AttnParams p_in) {
             const float p1 = __expf(s[nb][2 + e] * p.scale + a1 - lse1);
             float g0 = dp[nb][e], g1 = dp[nb][2 + e];
             if (p.drop_on) {
-              g0 = (e == 0 ? k00 : k01) ? g0 * p.drop_scale : 0.f;
-              g1 = (e == 0 ? k10 : k11) ? g1 * p.drop_scale : 0.f;
+              g0 = philox_u16(rnd, e | (nb << 2)) < p.drop_threshold ? g0 * p.drop_scale : 0.f;
+              g1 = philox_u16(rnd, e | 2 | (nb << 2)) < p.drop_threshold ? g1 * p.drop_scale : 0.f;
             }
             s[nb][e] = p0 * (g0 - D0) * p.scale;
             s[nb][2 + e] = p1 * (g1 - D1) * p.scale;
@@ -411,6 +401,11 @@ attention_bwd_kernel(const AttnParams p_in) {
         mma_a_yT(ka, sQ, q0, lane, st);    // S^T tile: rows = keys, cols = queries
         mma_a_yT(va, sdO, q0, lane, dpt);  // dP^T tile
         float pd[2][4];
+        uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (p.drop_on) {
+          rnd[0] = tile_rng(p, bh, q0 >> 4, k0 >> 4, Sq16 >> 4, Sk16 >> 4, ((2 * t) << 2) | (g >> 1));
+          rnd[1] = tile_rng(p, bh, q0 >> 4, k0 >> 4, Sq16 >> 4, Sk16 >> 4, ((2 * t + 1) << 2) | (g >> 1));
+        }
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
@@ -427,8 +422,9 @@ attention_bwd_kernel(const AttnParams p_in) {
             float g0 = dpt[nb][e], g1 = dpt[nb][2 + e];
             float pk0 = p0, pk1 = p1;
             if (p.drop_on) {
-              const int ii = i < p.Sq ? i : 0;
-              const bool kp0 = keep_one(p, bh, ii, j0r, Skq), kp1 = keep_one(p, bh, ii, j1r, Skq);
+              // element (query i, key j): word (j & 1) | ((i >> 3) & 1) << 1 | ((j >> 3) & 1) << 2 ; j = g (+8)
+              const bool kp0 = philox_u16(rnd[e], (g & 1) | (nb << 1)) < p.drop_threshold;
+              const bool kp1 = philox_u16(rnd[e], (g & 1) | (nb << 1) | 4) < p.drop_threshold;
               g0 = kp0 ? g0 * p.drop_scale : 0.f;
               g1 = kp1 ? g1 * p.drop_scale : 0.f;
               pk0 = kp0 ? p0 * p.drop_scale : 0.f;
@@ -489,7 +485,7 @@ static int fill_common(AttnParams& p, const void* q, long long ldq, const void* 
   p.mask_a = mask_a; p.mask_b = mask_b; p.Wa = Wa; p.Fb = Fb; p.Nb = Nb > 0 ? Nb : 1; p.all_pairs = all_pairs;
   p.n_seq = n_seq; p.heads = heads; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.scale = scale;
   p.drop_on = p_drop > 0.f;
-  p.drop_threshold = dropout_threshold(p_drop);
+  p.drop_threshold = dropout_threshold16(p_drop);
   p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "attention: dropout needs rng_state");
   p.seed = 0; p.stream = stream_id; p.rng = rng_state;

@@ -124,6 +124,25 @@ __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
   if (keep >= 1.0) return 0xFFFFFFFFu;
   return (uint32_t)(keep * 4294967296.0);
 }
+// 16-bit variant: an element is kept iff its 16 random bits are < threshold16, so one Philox4x32 call (128 bits)
+// decides 8 elements; P(keep) is exact to 2^-16, far below the sampling noise of any dropout mask.
+__host__ __device__ __forceinline__ uint32_t dropout_threshold16(float p) {
+  double keep = 1.0 - (double)p;
+  if (keep >= 1.0) return 65536u;
+  return (uint32_t)(keep * 65536.0 + 0.5);
+}
+// 16-bit word w (0..7) of a Philox output
+__device__ __forceinline__ uint32_t philox_u16(const uint4& r, int w) {
+  const uint32_t x = (w >> 1) == 0 ? r.x : (w >> 1) == 1 ? r.y : (w >> 1) == 2 ? r.z : r.w;
+  return (w & 1) ? (x >> 16) : (x & 0xFFFFu);
+}
+// keep-mask (bit j = keep element idx0 + j) of 8 consecutive elements, idx0 % 8 == 0: ONE Philox call
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t stream, uint64_t idx0, uint32_t thr16) {
+  const uint4 r = philox4x32(seed, stream, idx0 >> 3);
+  return ((r.x & 0xFFFFu) < thr16 ? 1u : 0u) | ((r.x >> 16) < thr16 ? 2u : 0u) | ((r.y & 0xFFFFu) < thr16 ? 4u : 0u) |
+         ((r.y >> 16) < thr16 ? 8u : 0u) | ((r.z & 0xFFFFu) < thr16 ? 16u : 0u) | ((r.z >> 16) < thr16 ? 32u : 0u) |
+         ((r.w & 0xFFFFu) < thr16 ? 64u : 0u) | ((r.w >> 16) < thr16 ? 128u : 0u);
+}
 
 // ----------------------------------------------------------------------------
 // mbarrier

@@ -55,10 +55,9 @@ __device__ __forceinline__ void st8h(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 __device__ __forceinline__ void emb_keep8(const EmbDrop& d, uint64_t idx0, bool (&k)[8]) {
-  const uint4 r0 = philox4x32(d.seed, d.stream, idx0 >> 2);
-  const uint4 r1 = philox4x32(d.seed, d.stream, (idx0 >> 2) + 1);
-  k[0] = r0.x < d.threshold; k[1] = r0.y < d.threshold; k[2] = r0.z < d.threshold; k[3] = r0.w < d.threshold;
-  k[4] = r1.x < d.threshold; k[5] = r1.y < d.threshold; k[6] = r1.z < d.threshold; k[7] = r1.w < d.threshold;
+  const uint32_t m = dropout_keep8(d.seed, d.stream, idx0, d.threshold);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = (m >> j) & 1u;
 }
 
 // z (registers) -> mean/rstd -> y ; shared by both forward kernels
@@ -369,7 +368,7 @@ embed_src_bwd_kernel(const bf16* __restrict__ dy, SrcCfg src, const float* __res
 static EmbDrop make_emb_drop(float p, const unsigned long long* rng, unsigned long long stream) {
   EmbDrop d;
   d.on = p > 0.f;
-  d.threshold = dropout_threshold(p);
+  d.threshold = dropout_threshold16(p);
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   d.seed = 0;
   d.stream = stream;

@@ -56,12 +56,11 @@ __device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
   return d;
 }
 
-// keep flags of 8 consecutive elements starting at flat index idx0 (idx0 % 8 == 0): two Philox calls
+// keep flags of 8 consecutive elements starting at flat index idx0 (idx0 % 8 == 0): one Philox call
 __device__ __forceinline__ void keep8(const DropCfg& d, uint64_t idx0, bool (&k)[8]) {
-  const uint4 r0 = philox4x32(d.seed, d.stream, idx0 >> 2);
-  const uint4 r1 = philox4x32(d.seed, d.stream, (idx0 >> 2) + 1);
-  k[0] = r0.x < d.threshold; k[1] = r0.y < d.threshold; k[2] = r0.z < d.threshold; k[3] = r0.w < d.threshold;
-  k[4] = r1.x < d.threshold; k[5] = r1.y < d.threshold; k[6] = r1.z < d.threshold; k[7] = r1.w < d.threshold;
+  const uint32_t m = dropout_keep8(d.seed, d.stream, idx0, d.threshold);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = (m >> j) & 1u;
 }
 
 template <typename TIn>
@@ -139,11 +138,7 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, co
 //   dx_dense (bf16, may be null): dz * keep/(1-p)          — gradient w.r.t. x under drop_mode 1
 //   dgamma, dbeta (fp32, atomically accumulated), dbias (fp32, optional) += column sums of dx_dense (or dz)
 __device__ __forceinline__ uint32_t keep8_mask(const DropCfg& d, uint64_t idx0) {
-  const uint4 r0 = philox4x32(d.seed, d.stream, idx0 >> 2);
-  const uint4 r1 = philox4x32(d.seed, d.stream, (idx0 >> 2) + 1);
-  return (r0.x < d.threshold ? 1u : 0u) | (r0.y < d.threshold ? 2u : 0u) | (r0.z < d.threshold ? 4u : 0u) |
-         (r0.w < d.threshold ? 8u : 0u) | (r1.x < d.threshold ? 16u : 0u) | (r1.y < d.threshold ? 32u : 0u) |
-         (r1.z < d.threshold ? 64u : 0u) | (r1.w < d.threshold ? 128u : 0u);
+  return dropout_keep8(d.seed, d.stream, idx0, d.threshold);
 }
 
 // one 8-wide vector of the row: z = pre-LayerNorm value, d = effective upstream gradient, keep = dropout bit mask
@@ -283,7 +278,7 @@ static int check_ln_shape(const char* what, int rows, int cols) {
 static DropCfg make_drop(int mode, float p, const unsigned long long* rng, unsigned long long stream) {
   DropCfg d;
   d.mode = (p > 0.f) ? mode : 0;
-  d.threshold = dropout_threshold(p);
+  d.threshold = dropout_threshold16(p);
   d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
   d.seed = 0;
   d.stream = stream;
