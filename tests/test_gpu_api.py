@@ -111,22 +111,22 @@ def test_flat_gradient_sinks_match_autograd_gradients():
 def test_training_steps_with_fused_optimizer_reduce_the_loss():
     from univl_b200.modules.optimization import BertAdam
     cfg = _small("ft_align", batch_size=4)
-    model = build_model(cfg, dropout=0.1)
+    model = build_model(cfg, sd=synth.make_state_dict(cfg, init_law=True), dropout=0.0)  # deterministic descent
     batch = to_device(synth.make_batch(cfg, seed=7))
     named = list(model.named_parameters())
     no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
     groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
               {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
-    opt = BertAdam(groups, lr=2e-4, warmup=0.1, t_total=50, max_grad_norm=1.0, model=model)
+    opt = BertAdam(groups, lr=1e-4, warmup=0.1, t_total=60, max_grad_norm=1.0, model=model)
     losses = []
-    for _ in range(12):
+    for _ in range(16):
         opt.zero_grad()
         loss = model(**batch)
         loss.backward()
         opt.step()
         losses.append(float(loss.detach()))
     assert all(l == l for l in losses)
-    assert sum(losses[-3:]) / 3 < sum(losses[:3]) / 3 - 1e-3, losses
+    assert losses[-1] < losses[0] - 1e-3 and min(losses) == min(losses[-4:]), losses
     assert opt.get_lr()[0] > 0
 
 

@@ -139,6 +139,9 @@ __device__ __forceinline__ uint4 tile_rng(const AttnParams& p, long long bh, int
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
+// NKB > 0: the whole score row (<= NKB 16-key blocks) stays in registers — one QK^T pass, exact softmax, 2 * NKB
+// independent accumulator chains for the tensor pipe.  NKB == 0: 16-key chunks with a stats pre-pass (any Sk <= 256).
+template <int NKB>
 __global__ void __launch_bounds__(ATT_FWD_WARPS * 32)
 attention_fwd_kernel(const AttnParams p_in) {
   AttnParams p = p_in;
@@ -169,6 +172,98 @@ attention_fwd_kernel(const AttnParams p_in) {
     uint32_t qa[4][4];
     load_a_frags(sQ, q0, lane, qa);
     const int i0 = q0 + g, i1 = q0 + g + 8;
+    if constexpr (NKB > 0) {
+      const int nkb = Sk16 >> 4;
+      float s[NKB][2][4];
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb)
+        if (kb < nkb) mma_a_yT(qa, sK, kb * 16, lane, s[kb]);
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb)
+        if (kb < nkb) {
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = kb * 16 + nb * 8 + 2 * t + e;
+              const float ma = madd[j];
+              float a0 = ma, a1 = ma;
+              if (p.causal) {
+                if (j > i0 && a0 == 0.f) a0 = -10000.f;
+                if (j > i1 && a1 == 0.f) a1 = -10000.f;
+              }
+              s[kb][nb][e] = s[kb][nb][e] * p.scale + a0;
+              s[kb][nb][2 + e] = s[kb][nb][2 + e] * p.scale + a1;
+              mx0 = fmaxf(mx0, s[kb][nb][e]);
+              mx1 = fmaxf(mx1, s[kb][nb][2 + e]);
+            }
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb)
+        if (kb < nkb) {
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              s[kb][nb][e] = __expf(s[kb][nb][e] - mx0);
+              s[kb][nb][2 + e] = __expf(s[kb][nb][2 + e] - mx1);
+              sum0 += s[kb][nb][e];
+              sum1 += s[kb][nb][2 + e];
+            }
+        }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float r0 = 1.0f / sum0, r1 = 1.0f / sum1;
+      float o[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[nb][e] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb)
+        if (kb < nkb) {
+          uint4 rnd = make_uint4(0, 0, 0, 0);
+          if (p.drop_on) rnd = tile_rng(p, bh, q0 >> 4, kb, Sq16 >> 4, Sk16 >> 4, lane);
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float p0 = s[kb][nb][e] * r0, p1 = s[kb][nb][2 + e] * r1;
+              if (p.drop_on) {
+                p0 = philox_u16(rnd, e | (nb << 2)) < p.drop_threshold ? p0 * p.drop_scale : 0.f;
+                p1 = philox_u16(rnd, e | 2 | (nb << 2)) < p.drop_threshold ? p1 * p.drop_scale : 0.f;
+              }
+              s[kb][nb][e] = p0;
+              s[kb][nb][2 + e] = p1;
+            }
+          uint32_t pa[4];
+          pa[0] = pack_bf16x2(s[kb][0][0], s[kb][0][1]);
+          pa[1] = pack_bf16x2(s[kb][0][2], s[kb][0][3]);
+          pa[2] = pack_bf16x2(s[kb][1][0], s[kb][1][1]);
+          pa[3] = pack_bf16x2(s[kb][1][2], s[kb][1][3]);
+          mma_p_z(pa, sV, kb * 16, lane, o);
+        }
+      bf16* orow0 = p.o + ((long long)seq * p.Sq + i0) * p.ldo + h * HD;
+      bf16* orow1 = p.o + ((long long)seq * p.Sq + i1) * p.ldo + h * HD;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        if (i0 < p.Sq) *reinterpret_cast<uint32_t*>(orow0 + nb * 8 + 2 * t) = pack_bf16x2(o[nb][0], o[nb][1]);
+        if (i1 < p.Sq) *reinterpret_cast<uint32_t*>(orow1 + nb * 8 + 2 * t) = pack_bf16x2(o[nb][2], o[nb][3]);
+      }
+      if (t == 0 && p.lse != nullptr) {
+        if (i0 < p.Sq) p.lse[bh * p.Sq + i0] = mx0 + __logf(sum0);
+        if (i1 < p.Sq) p.lse[bh * p.Sq + i1] = mx1 + __logf(sum1);
+      }
+      continue;
+    }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     // pass 1: row max and sum of exponentials
     for (int j0 = 0; j0 < Sk16; j0 += 16) {
@@ -513,10 +608,14 @@ extern "C" int univl_attention_fwd(const void* q, long long ldq, const void* k, 
   p.o = (bf16*)o; p.ldo = ldo; p.lse = lse;
   const int Sq16 = (Sq + 15) & ~15, Sk16 = (Sk + 15) & ~15;
   const size_t smem = (size_t)(Sq16 + 2 * Sk16) * LDS * 2 + (size_t)Sk16 * 4;
-  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nkb = Sk16 / 16;
+  void (*kern)(const AttnParams) = nkb <= 3 ? attention_fwd_kernel<3>
+                                   : nkb <= 6 ? attention_fwd_kernel<6>
+                                   : nkb <= 8 ? attention_fwd_kernel<8> : attention_fwd_kernel<0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_fwd smem attribute: %s", cudaGetErrorString(e));
   const int fwd_warps = (Sq16 / 16) < ATT_FWD_WARPS ? (Sq16 / 16) : ATT_FWD_WARPS;
-  attention_fwd_kernel<<<n_seq * heads, fwd_warps * 32, smem, (cudaStream_t)stream>>>(p);
+  kern<<<n_seq * heads, fwd_warps * 32, smem, (cudaStream_t)stream>>>(p);
   UNIVL_CHECK_LAUNCH("attention_fwd");
   return UNIVL_OK;
 }
