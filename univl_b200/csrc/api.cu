@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace univl {
 
@@ -14,6 +15,15 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UNIVL_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // measured neutral on the FT-Align step (graph replay): opt-in
+  }
+  return v == 1;
 }
 
 }  // namespace univl

@@ -42,6 +42,7 @@ struct AttnParams {
   long long lddo;
   bf16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
+  int share_tiles;  // backward: 1 = query-major pass shares P_drop / dS with the key-major pass through smem
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -144,6 +145,8 @@ __device__ __forceinline__ uint4 tile_rng(const AttnParams& p, long long bh, int
 template <int NKB>
 __global__ void __launch_bounds__(ATT_FWD_WARPS * 32)
 attention_fwd_kernel(const AttnParams p_in) {
+  pdl_trigger();
+  pdl_wait();
   AttnParams p = p_in;
   if (p.drop_on && p.rng != nullptr) {
     p.seed = p.rng[0];
@@ -364,11 +367,225 @@ attention_fwd_kernel(const AttnParams p_in) {
   }
 }
 
+// ---- backward tasks ---------------------------------------------------------------------------------------------
+struct BwdSmem {
+  const bf16 *sQ, *sdO, *sK, *sV;
+  const float *madd, *sLse, *sD;
+  bf16 *sP, *sdS;  // SHARE mode: dropped probabilities / dS, [Sq16][ldp]
+  int ldp;
+};
+
+template <bool SHARE>
+__device__ __forceinline__ void bwd_dq_task(const AttnParams& p, const BwdSmem& sm, int task, int lane, int seq, int h,
+                                            long long bh, int Sq16, int Sk16) {
+  const bf16 *sQ = sm.sQ, *sdO = sm.sdO, *sK = sm.sK, *sV = sm.sV;
+  const float *madd = sm.madd, *sLse = sm.sLse, *sD = sm.sD;
+  bf16 *sP = sm.sP, *sdS = sm.sdS;
+  const int ldp = sm.ldp;
+  (void)sP; (void)sdS; (void)ldp;  // used only when SHARE
+  // ---------------- dQ for 16 query rows ----------------
+  const int q0 = task * 16;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t qa[4][4], da[4][4];
+  load_a_frags(sQ, q0, lane, qa);
+  load_a_frags(sdO, q0, lane, da);
+  const int i0 = q0 + g, i1 = q0 + g + 8;
+  const float lse0 = sLse[i0], lse1 = sLse[i1], D0 = sD[i0], D1 = sD[i1];
+  float acc[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
+  for (int j0 = 0; j0 < Sk16; j0 += 16) {
+    float s[2][4], dp[2][4];
+    mma_a_yT(qa, sK, j0, lane, s);
+    mma_a_yT(da, sV, j0, lane, dp);
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (p.drop_on) rnd = tile_rng(p, bh, q0 >> 4, j0 >> 4, Sq16 >> 4, Sk16 >> 4, lane);
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+      const int jb = j0 + nb * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = jb + e;
+        float ma = madd[j];
+        float a0 = ma, a1 = ma;
+        if (p.causal) {
+          if (j > i0 && a0 == 0.f) a0 = -10000.f;
+          if (j > i1 && a1 == 0.f) a1 = -10000.f;
+        }
+        const float p0 = __expf(s[nb][e] * p.scale + a0 - lse0);
+        const float p1 = __expf(s[nb][2 + e] * p.scale + a1 - lse1);
+        float g0 = dp[nb][e], g1 = dp[nb][2 + e];
+        float pk0 = p0, pk1 = p1;
+        if (p.drop_on) {
+          const bool kp0 = philox_u16(rnd, e | (nb << 2)) < p.drop_threshold;
+          const bool kp1 = philox_u16(rnd, e | 2 | (nb << 2)) < p.drop_threshold;
+          g0 = kp0 ? g0 * p.drop_scale : 0.f;
+          g1 = kp1 ? g1 * p.drop_scale : 0.f;
+          pk0 = kp0 ? p0 * p.drop_scale : 0.f;
+          pk1 = kp1 ? p1 * p.drop_scale : 0.f;
+        }
+        s[nb][e] = p0 * (g0 - D0) * p.scale;
+        s[nb][2 + e] = p1 * (g1 - D1) * p.scale;
+        dp[nb][e] = pk0;  // dP is consumed: reuse its registers for the dropped probabilities
+        dp[nb][2 + e] = pk1;
+      }
+      if (SHARE) {
+        *reinterpret_cast<uint32_t*>(sP + i0 * ldp + jb) = pack_bf16x2(dp[nb][0], dp[nb][1]);
+        *reinterpret_cast<uint32_t*>(sP + i1 * ldp + jb) = pack_bf16x2(dp[nb][2], dp[nb][3]);
+        *reinterpret_cast<uint32_t*>(sdS + i0 * ldp + jb) = pack_bf16x2(s[nb][0], s[nb][1]);
+        *reinterpret_cast<uint32_t*>(sdS + i1 * ldp + jb) = pack_bf16x2(s[nb][2], s[nb][3]);
+      }
+    }
+    uint32_t pa[4];
+    pa[0] = pack_bf16x2(s[0][0], s[0][1]);
+    pa[1] = pack_bf16x2(s[0][2], s[0][3]);
+    pa[2] = pack_bf16x2(s[1][0], s[1][1]);
+    pa[3] = pack_bf16x2(s[1][2], s[1][3]);
+    mma_p_z(pa, sK, j0, lane, acc);
+  }
+  bf16* r0 = p.dq + ((long long)seq * p.Sq + i0) * p.lddq + h * HD;
+  bf16* r1 = p.dq + ((long long)seq * p.Sq + i1) * p.lddq + h * HD;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    if (i0 < p.Sq) *reinterpret_cast<uint32_t*>(r0 + nb * 8 + 2 * t) = pack_bf16x2(acc[nb][0], acc[nb][1]);
+    if (i1 < p.Sq) *reinterpret_cast<uint32_t*>(r1 + nb * 8 + 2 * t) = pack_bf16x2(acc[nb][2], acc[nb][3]);
+  }
+}
+
+// key-major pass that recomputes the transposed score / dP tiles (any S <= 256)
+__device__ __forceinline__ void bwd_dkdv_task_recompute(const AttnParams& p, const BwdSmem& sm, int task, int lane,
+                                                        int seq, int h, long long bh, int Sq16, int Sk16) {
+  const bf16 *sQ = sm.sQ, *sdO = sm.sdO, *sK = sm.sK, *sV = sm.sV;
+  const float *madd = sm.madd, *sLse = sm.sLse, *sD = sm.sD;
+  // ---------------- dK, dV for 16 key rows (transposed tiles) ----------------
+  const int k0 = task * 16;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t ka[4][4], va[4][4];
+  load_a_frags(sK, k0, lane, ka);
+  load_a_frags(sV, k0, lane, va);
+  const int j0r = k0 + g, j1r = k0 + g + 8;
+  const float ma0 = madd[j0r], ma1 = madd[j1r];
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dk[nb][e] = dv[nb][e] = 0.f;
+  for (int q0 = 0; q0 < Sq16; q0 += 16) {
+    float st[2][4], dpt[2][4];
+    mma_a_yT(ka, sQ, q0, lane, st);    // S^T tile: rows = keys, cols = queries
+    mma_a_yT(va, sdO, q0, lane, dpt);  // dP^T tile
+    float pd[2][4];
+    uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (p.drop_on) {
+      rnd[0] = tile_rng(p, bh, q0 >> 4, k0 >> 4, Sq16 >> 4, Sk16 >> 4, ((2 * t) << 2) | (g >> 1));
+      rnd[1] = tile_rng(p, bh, q0 >> 4, k0 >> 4, Sq16 >> 4, Sk16 >> 4, ((2 * t + 1) << 2) | (g >> 1));
+    }
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = q0 + nb * 8 + 2 * t + e;
+        const float lse = sLse[i], D = sD[i];
+        float a0 = ma0, a1 = ma1;
+        if (p.causal) {
+          if (j0r > i && a0 == 0.f) a0 = -10000.f;
+          if (j1r > i && a1 == 0.f) a1 = -10000.f;
+        }
+        const float p0 = __expf(st[nb][e] * p.scale + a0 - lse);
+        const float p1 = __expf(st[nb][2 + e] * p.scale + a1 - lse);
+        float g0 = dpt[nb][e], g1 = dpt[nb][2 + e];
+        float pk0 = p0, pk1 = p1;
+        if (p.drop_on) {
+          // element (query i, key j): word (j & 1) | ((i >> 3) & 1) << 1 | ((j >> 3) & 1) << 2 ; j = g (+8)
+          const bool kp0 = philox_u16(rnd[e], (g & 1) | (nb << 1)) < p.drop_threshold;
+          const bool kp1 = philox_u16(rnd[e], (g & 1) | (nb << 1) | 4) < p.drop_threshold;
+          g0 = kp0 ? g0 * p.drop_scale : 0.f;
+          g1 = kp1 ? g1 * p.drop_scale : 0.f;
+          pk0 = kp0 ? p0 * p.drop_scale : 0.f;
+          pk1 = kp1 ? p1 * p.drop_scale : 0.f;
+        }
+        pd[nb][e] = pk0;
+        pd[nb][2 + e] = pk1;
+        st[nb][e] = p0 * (g0 - D) * p.scale;
+        st[nb][2 + e] = p1 * (g1 - D) * p.scale;
+      }
+    uint32_t pa[4], sa[4];
+    pa[0] = pack_bf16x2(pd[0][0], pd[0][1]);
+    pa[1] = pack_bf16x2(pd[0][2], pd[0][3]);
+    pa[2] = pack_bf16x2(pd[1][0], pd[1][1]);
+    pa[3] = pack_bf16x2(pd[1][2], pd[1][3]);
+    sa[0] = pack_bf16x2(st[0][0], st[0][1]);
+    sa[1] = pack_bf16x2(st[0][2], st[0][3]);
+    sa[2] = pack_bf16x2(st[1][0], st[1][1]);
+    sa[3] = pack_bf16x2(st[1][2], st[1][3]);
+    mma_p_z(pa, sdO, q0, lane, dv);
+    mma_p_z(sa, sQ, q0, lane, dk);
+  }
+  bf16* kr0 = p.dk + ((long long)seq * p.Sk + j0r) * p.lddk + h * HD;
+  bf16* kr1 = p.dk + ((long long)seq * p.Sk + j1r) * p.lddk + h * HD;
+  bf16* vr0 = p.dv + ((long long)seq * p.Sk + j0r) * p.lddv + h * HD;
+  bf16* vr1 = p.dv + ((long long)seq * p.Sk + j1r) * p.lddv + h * HD;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    if (j0r < p.Sk) {
+      *reinterpret_cast<uint32_t*>(kr0 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][0], dk[nb][1]);
+      *reinterpret_cast<uint32_t*>(vr0 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][0], dv[nb][1]);
+    }
+    if (j1r < p.Sk) {
+      *reinterpret_cast<uint32_t*>(kr1 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][2], dk[nb][3]);
+      *reinterpret_cast<uint32_t*>(vr1 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][2], dv[nb][3]);
+    }
+  }
+}
+
+// key-major pass on the tiles the query-major pass left in shared memory: dV = P_drop^T dO, dK = dS^T Q.  The A
+// operand of both products is a transposed 16 x 16 block of a [query][key] matrix = ldmatrix.trans.
+__device__ __forceinline__ void bwd_dkdv_task_shared(const AttnParams& p, const BwdSmem& sm, int task, int lane, int seq,
+                                                     int h, int Sq16) {
+  const int k0 = task * 16;
+  const int g = lane >> 2, t = lane & 3;
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dk[nb][e] = dv[nb][e] = 0.f;
+  // matrix m of the x4 load: query half (m >> 1), key half (m & 1)
+  const int row_in = (lane & 7) + ((lane >> 4) & 1) * 8;
+  const int col = k0 + ((lane >> 3) & 1) * 8;
+  for (int q0 = 0; q0 < Sq16; q0 += 16) {
+    uint32_t pa[4], sa[4];
+    ldsm_x4_t(smem_u32(sm.sP + (q0 + row_in) * sm.ldp + col), pa);
+    ldsm_x4_t(smem_u32(sm.sdS + (q0 + row_in) * sm.ldp + col), sa);
+    mma_p_z(pa, sm.sdO, q0, lane, dv);
+    mma_p_z(sa, sm.sQ, q0, lane, dk);
+  }
+  const int j0r = k0 + g, j1r = k0 + g + 8;
+  bf16* kr0 = p.dk + ((long long)seq * p.Sk + j0r) * p.lddk + h * HD;
+  bf16* kr1 = p.dk + ((long long)seq * p.Sk + j1r) * p.lddk + h * HD;
+  bf16* vr0 = p.dv + ((long long)seq * p.Sk + j0r) * p.lddv + h * HD;
+  bf16* vr1 = p.dv + ((long long)seq * p.Sk + j1r) * p.lddv + h * HD;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    if (j0r < p.Sk) {
+      *reinterpret_cast<uint32_t*>(kr0 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][0], dk[nb][1]);
+      *reinterpret_cast<uint32_t*>(vr0 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][0], dv[nb][1]);
+    }
+    if (j1r < p.Sk) {
+      *reinterpret_cast<uint32_t*>(kr1 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][2], dk[nb][3]);
+      *reinterpret_cast<uint32_t*>(vr1 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][2], dv[nb][3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATT_BWD_WARPS * 32)
 attention_bwd_kernel(const AttnParams p_in) {
+  pdl_trigger();
+  pdl_wait();
   AttnParams p = p_in;
   if (p.drop_on && p.rng != nullptr) {
     p.seed = p.rng[0];
@@ -421,142 +638,19 @@ attention_bwd_kernel(const AttnParams p_in) {
   __syncthreads();
 
   const int nQ = Sq16 >> 4, nK = Sk16 >> 4;
-  for (int task = warp; task < nQ + nK; task += (int)(blockDim.x >> 5)) {
-    if (task < nQ) {
-      // ---------------- dQ for 16 query rows ----------------
-      const int q0 = task * 16;
-      uint32_t qa[4][4], da[4][4];
-      load_a_frags(sQ, q0, lane, qa);
-      load_a_frags(sdO, q0, lane, da);
-      const int i0 = q0 + g, i1 = q0 + g + 8;
-      const float lse0 = sLse[i0], lse1 = sLse[i1], D0 = sD[i0], D1 = sD[i1];
-      float acc[8][4];
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
-      for (int j0 = 0; j0 < Sk16; j0 += 16) {
-        float s[2][4], dp[2][4];
-        mma_a_yT(qa, sK, j0, lane, s);
-        mma_a_yT(da, sV, j0, lane, dp);
-        uint4 rnd = make_uint4(0, 0, 0, 0);
-        if (p.drop_on) rnd = tile_rng(p, bh, q0 >> 4, j0 >> 4, Sq16 >> 4, Sk16 >> 4, lane);
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          const int jb = j0 + nb * 8 + 2 * t;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = jb + e;
-            float ma = madd[j];
-            float a0 = ma, a1 = ma;
-            if (p.causal) {
-              if (j > i0 && a0 == 0.f) a0 = -10000.f;
-              if (j > i1 && a1 == 0.f) a1 = -10000.f;
-            }
-            const float p0 = __expf(s[nb][e] * p.scale + a0 - lse0);
-            const float p1 = __expf(s[nb][2 + e] * p.scale + a1 - lse1);
-            float g0 = dp[nb][e], g1 = dp[nb][2 + e];
-            if (p.drop_on) {
-              g0 = philox_u16(rnd, e | (nb << 2)) < p.drop_threshold ? g0 * p.drop_scale : 0.f;
-              g1 = philox_u16(rnd, e | 2 | (nb << 2)) < p.drop_threshold ? g1 * p.drop_scale : 0.f;
-            }
-            s[nb][e] = p0 * (g0 - D0) * p.scale;
-            s[nb][2 + e] = p1 * (g1 - D1) * p.scale;
-          }
-        }
-        uint32_t pa[4];
-        pa[0] = pack_bf16x2(s[0][0], s[0][1]);
-        pa[1] = pack_bf16x2(s[0][2], s[0][3]);
-        pa[2] = pack_bf16x2(s[1][0], s[1][1]);
-        pa[3] = pack_bf16x2(s[1][2], s[1][3]);
-        mma_p_z(pa, sK, j0, lane, acc);
-      }
-      bf16* r0 = p.dq + ((long long)seq * p.Sq + i0) * p.lddq + h * HD;
-      bf16* r1 = p.dq + ((long long)seq * p.Sq + i1) * p.lddq + h * HD;
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        if (i0 < p.Sq) *reinterpret_cast<uint32_t*>(r0 + nb * 8 + 2 * t) = pack_bf16x2(acc[nb][0], acc[nb][1]);
-        if (i1 < p.Sq) *reinterpret_cast<uint32_t*>(r1 + nb * 8 + 2 * t) = pack_bf16x2(acc[nb][2], acc[nb][3]);
-      }
-    } else {
-      // ---------------- dK, dV for 16 key rows (transposed tiles) ----------------
-      const int k0 = (task - nQ) * 16;
-      uint32_t ka[4][4], va[4][4];
-      load_a_frags(sK, k0, lane, ka);
-      load_a_frags(sV, k0, lane, va);
-      const int j0r = k0 + g, j1r = k0 + g + 8;
-      const float ma0 = madd[j0r], ma1 = madd[j1r];
-      float dk[8][4], dv[8][4];
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dk[nb][e] = dv[nb][e] = 0.f;
-      for (int q0 = 0; q0 < Sq16; q0 += 16) {
-        float st[2][4], dpt[2][4];
-        mma_a_yT(ka, sQ, q0, lane, st);    // S^T tile: rows = keys, cols = queries
-        mma_a_yT(va, sdO, q0, lane, dpt);  // dP^T tile
-        float pd[2][4];
-        uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (p.drop_on) {
-          rnd[0] = tile_rng(p, bh, q0 >> 4, k0 >> 4, Sq16 >> 4, Sk16 >> 4, ((2 * t) << 2) | (g >> 1));
-          rnd[1] = tile_rng(p, bh, q0 >> 4, k0 >> 4, Sq16 >> 4, Sk16 >> 4, ((2 * t + 1) << 2) | (g >> 1));
-        }
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = q0 + nb * 8 + 2 * t + e;
-            const float lse = sLse[i], D = sD[i];
-            float a0 = ma0, a1 = ma1;
-            if (p.causal) {
-              if (j0r > i && a0 == 0.f) a0 = -10000.f;
-              if (j1r > i && a1 == 0.f) a1 = -10000.f;
-            }
-            const float p0 = __expf(st[nb][e] * p.scale + a0 - lse);
-            const float p1 = __expf(st[nb][2 + e] * p.scale + a1 - lse);
-            float g0 = dpt[nb][e], g1 = dpt[nb][2 + e];
-            float pk0 = p0, pk1 = p1;
-            if (p.drop_on) {
-              // element (query i, key j): word (j & 1) | ((i >> 3) & 1) << 1 | ((j >> 3) & 1) << 2 ; j = g (+8)
-              const bool kp0 = philox_u16(rnd[e], (g & 1) | (nb << 1)) < p.drop_threshold;
-              const bool kp1 = philox_u16(rnd[e], (g & 1) | (nb << 1) | 4) < p.drop_threshold;
-              g0 = kp0 ? g0 * p.drop_scale : 0.f;
-              g1 = kp1 ? g1 * p.drop_scale : 0.f;
-              pk0 = kp0 ? p0 * p.drop_scale : 0.f;
-              pk1 = kp1 ? p1 * p.drop_scale : 0.f;
-            }
-            pd[nb][e] = pk0;
-            pd[nb][2 + e] = pk1;
-            st[nb][e] = p0 * (g0 - D) * p.scale;
-            st[nb][2 + e] = p1 * (g1 - D) * p.scale;
-          }
-        uint32_t pa[4], sa[4];
-        pa[0] = pack_bf16x2(pd[0][0], pd[0][1]);
-        pa[1] = pack_bf16x2(pd[0][2], pd[0][3]);
-        pa[2] = pack_bf16x2(pd[1][0], pd[1][1]);
-        pa[3] = pack_bf16x2(pd[1][2], pd[1][3]);
-        sa[0] = pack_bf16x2(st[0][0], st[0][1]);
-        sa[1] = pack_bf16x2(st[0][2], st[0][3]);
-        sa[2] = pack_bf16x2(st[1][0], st[1][1]);
-        sa[3] = pack_bf16x2(st[1][2], st[1][3]);
-        mma_p_z(pa, sdO, q0, lane, dv);
-        mma_p_z(sa, sQ, q0, lane, dk);
-      }
-      bf16* kr0 = p.dk + ((long long)seq * p.Sk + j0r) * p.lddk + h * HD;
-      bf16* kr1 = p.dk + ((long long)seq * p.Sk + j1r) * p.lddk + h * HD;
-      bf16* vr0 = p.dv + ((long long)seq * p.Sk + j0r) * p.lddv + h * HD;
-      bf16* vr1 = p.dv + ((long long)seq * p.Sk + j1r) * p.lddv + h * HD;
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        if (j0r < p.Sk) {
-          *reinterpret_cast<uint32_t*>(kr0 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][0], dk[nb][1]);
-          *reinterpret_cast<uint32_t*>(vr0 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][0], dv[nb][1]);
-        }
-        if (j1r < p.Sk) {
-          *reinterpret_cast<uint32_t*>(kr1 + nb * 8 + 2 * t) = pack_bf16x2(dk[nb][2], dk[nb][3]);
-          *reinterpret_cast<uint32_t*>(vr1 + nb * 8 + 2 * t) = pack_bf16x2(dv[nb][2], dv[nb][3]);
-        }
-      }
+  const int nw = (int)(blockDim.x >> 5);
+  BwdSmem sm{sQ, sdO, sK, sV, madd, sLse, sD, nullptr, nullptr, Sk16 + 8};
+  if (p.share_tiles) {
+    // S <= 128: the query-major pass leaves P_drop and dS in shared memory; the key-major pass only multiplies
+    sm.sP = reinterpret_cast<bf16*>(sD + Sq16);
+    sm.sdS = sm.sP + Sq16 * sm.ldp;
+    for (int task = warp; task < nQ; task += nw) bwd_dq_task<true>(p, sm, task, lane, seq, h, bh, Sq16, Sk16);
+    __syncthreads();
+    for (int task = warp; task < nK; task += nw) bwd_dkdv_task_shared(p, sm, task, lane, seq, h, Sq16);
+  } else {
+    for (int task = warp; task < nQ + nK; task += nw) {
+      if (task < nQ) bwd_dq_task<false>(p, sm, task, lane, seq, h, bh, Sq16, Sk16);
+      else bwd_dkdv_task_recompute(p, sm, task - nQ, lane, seq, h, bh, Sq16, Sk16);
     }
   }
 }
@@ -615,7 +709,7 @@ extern "C" int univl_attention_fwd(const void* q, long long ldq, const void* k, 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_fwd smem attribute: %s", cudaGetErrorString(e));
   const int fwd_warps = (Sq16 / 16) < ATT_FWD_WARPS ? (Sq16 / 16) : ATT_FWD_WARPS;
-  kern<<<n_seq * heads, fwd_warps * 32, smem, (cudaStream_t)stream>>>(p);
+  launch_kernel(kern, dim3(n_seq * heads), dim3(fwd_warps * 32), smem, (cudaStream_t)stream, p);
   UNIVL_CHECK_LAUNCH("attention_fwd");
   return UNIVL_OK;
 }
@@ -640,12 +734,15 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   const int Sq16 = (Sq + 15) & ~15, Sk16 = (Sk + 15) & ~15;
-  const size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16) * 4;
+  size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16) * 4;
+  p.share_tiles = (Sq16 <= 128 && Sk16 <= 128) ? 1 : 0;
+  if (p.share_tiles) smem += (size_t)2 * Sq16 * (Sk16 + 8) * 2;
   cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_bwd smem attribute: %s", cudaGetErrorString(e));
-  const int tasks = Sq16 / 16 + Sk16 / 16;
+  int tasks = Sq16 / 16 + Sk16 / 16;
+  if (p.share_tiles) tasks = Sq16 / 16 > Sk16 / 16 ? Sq16 / 16 : Sk16 / 16;  // the two passes run one after the other
   const int bwd_warps = tasks < ATT_BWD_WARPS ? tasks : ATT_BWD_WARPS;
-  attention_bwd_kernel<<<n_seq * heads, bwd_warps * 32, smem, (cudaStream_t)stream>>>(p);
+  launch_kernel(attention_bwd_kernel, dim3(n_seq * heads), dim3(bwd_warps * 32), smem, (cudaStream_t)stream, p);
   UNIVL_CHECK_LAUNCH("attention_bwd");
   return UNIVL_OK;
 }

@@ -38,6 +38,34 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 // ----------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every hot kernel is launched with the programmatic-stream-serialization
+// attribute, calls pdl_trigger() on entry (the NEXT kernel's CTAs may become resident as soon as all of ours have
+// started) and pdl_wait() before its first global-memory access (blocks until the previous kernel has completed and
+// flushed).  Launch latency and per-CTA set-up of kernel N+1 overlap the tail of kernel N — the text / visual encoder
+// layers are ~25 kernels of 5-15 us each.  Opt-in with UNIVL_PDL=1 (without the attribute the device calls are no-ops);
+// measured neutral (1806 vs 1816 samples/s) under CUDA-graph replay, so it is off by default.
+// ----------------------------------------------------------------------------
+bool pdl_enabled();  // api.cu
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ----------------------------------------------------------------------------
 // generic helpers
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -79,34 +107,16 @@ __device__ __forceinline__ void erf_exp_terms(float x, float& erf_abs, float& ga
   poly = fmaf(poly, t, 0.254829592f);
   erf_abs = fmaf(-poly * t, gauss, 1.0f);                        // erf(|x| / sqrt(2))
 }
-// Epilogue-rate evaluation of the SAME function.  The fused GEMM epilogues run on 8 warps per SM and the A&S form
-// above costs ~17 issue slots per element (ncu: 52 % issue-active on the FFN1+GELU GEMM, tensor pipe starved), so the
-// hot path evaluates the normal CDF as
-//     Phi(x) = 0.5 * (1 + erf(x / sqrt(2)))  ~=  0.5 * (1 + tanh(x * (c1 + c3 x^2 + c5 x^4))),   |x| <= 6 (clamped)
-// with a minimax fit of THE ERF CDF (not OpenAI's tanh-GELU constants): max |Phi error| 1.2e-4 in exact arithmetic,
-// + MUFU.TANH's 2^-11 relative error => |gelu error| <= ~4e-4 * |x|, a fifth of the bf16 output's half-ulp.
-// 9 issue slots for gelu, 13 for gelu'.  (oracle / reference keep the exact erf; parity tests bound the difference.)
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float normal_cdf_tanh_term(float x) {  // tanh term t with Phi(x) = 0.5 * (1 + t)
-  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-  const float x2 = xc * xc;
-  float p = fmaf(-0.0003773985605701086f, x2, 0.037207594064468906f);
-  p = fmaf(p, x2, 0.7971406982094169f);
-  return tanh_approx(xc * p);
-}
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float h = 0.5f * x;
-  return fmaf(h, normal_cdf_tanh_term(x), h);
+  float e, g;
+  erf_exp_terms(x, e, g);
+  return 0.5f * x * (1.0f + copysignf(e, x));
 }
 // d/dx gelu_erf(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float t = normal_cdf_tanh_term(x);
-  const float gauss = exp2f(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2)
-  return fmaf(x * 0.39894228040143267794f, gauss, fmaf(0.5f, t, 0.5f));
+  float e, g;
+  erf_exp_terms(x, e, g);
+  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + copysignf(e, x)));
 }
 
 // ----------------------------------------------------------------------------

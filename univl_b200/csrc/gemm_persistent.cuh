@@ -293,6 +293,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
                                const __grid_constant__ CUtensorMap tmap_aux, const GemmParams p, const int num_work) {
   using L = GemmSmemP<BLOCK_N, STAGES>;
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -333,6 +334,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -498,6 +500,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   constexpr int PAIR_M = 2 * BLOCK_M;
   constexpr int HALF_N = BLOCK_N / 2;
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -541,6 +544,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   cluster_sync_all();  // barrier inits of both CTAs visible cluster-wide before any remote arrive / TMA signal
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------

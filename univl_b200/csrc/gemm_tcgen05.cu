@@ -358,7 +358,8 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
       (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
   const int grid = (int)(work < sms ? work : sms);
-  kern<<<grid, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, to, tx, p, (int)work);
+  e = launch_kernel(kern, dim3(grid), dim3(GEMM_P_THREADS), (size_t)L::DYN_BYTES, stream, ta, tb, to, tx, p, (int)work);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   UNIVL_CHECK_LAUNCH("gemm_tcgen05_persistent");
   return UNIVL_OK;
 }
@@ -386,7 +387,8 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
       (long long)((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
   const int pairs = (int)(work < sms / 2 ? work : sms / 2);
-  kern<<<2 * pairs, GEMM_P_THREADS, L::DYN_BYTES, stream>>>(ta, tb, to, tx, p, (int)work);
+  e = launch_kernel(kern, dim3(2 * pairs), dim3(GEMM_P_THREADS), (size_t)L::DYN_BYTES, stream, ta, tb, to, tx, p, (int)work);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   UNIVL_CHECK_LAUNCH("gemm_tcgen05_2cta");
   return UNIVL_OK;
 }

@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows, int cols, float eps, DropCfg drop_in) {
+  pdl_trigger();
+  pdl_wait();
   const DropCfg drop = resolve_drop(drop_in);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = cols >> 8;
@@ -183,6 +185,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                      const float* __restrict__ rstd_in, bf16* __restrict__ dx_res, bf16* __restrict__ dx_dense,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int rows,
                      DropCfg drop_in) {
+  pdl_trigger();
+  pdl_wait();
   const DropCfg drop = resolve_drop(drop_in);
   __shared__ float red[LNB_WARPS][32 * 8 + 1];
   constexpr int cols = NVEC * 256;
@@ -261,10 +265,10 @@ static void launch_ln_bwd(int grid, cudaStream_t st, const bf16* dy, const bf16*
                           const float* gamma, const float* mean, const float* rstd, bf16* dx_res, bf16* dx_dense,
                           float* dgamma, float* dbeta, float* dbias, int rows, int cols, DropCfg drop) {
   switch (cols >> 8) {
-    case 1: layernorm_bwd_kernel<TIn, 1><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
-    case 2: layernorm_bwd_kernel<TIn, 2><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
-    case 3: layernorm_bwd_kernel<TIn, 3><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
-    default: layernorm_bwd_kernel<TIn, 4><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 1: launch_kernel(layernorm_bwd_kernel<TIn, 1>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 2: launch_kernel(layernorm_bwd_kernel<TIn, 2>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 3: launch_kernel(layernorm_bwd_kernel<TIn, 3>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    default: launch_kernel(layernorm_bwd_kernel<TIn, 4>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
   }
 }
 
@@ -311,9 +315,9 @@ extern "C" int univl_layernorm_fwd(const void* x, const void* res, const float* 
   UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "layernorm_fwd: dropout needs rng_state");
   UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && drop_mode >= 0 && drop_mode <= 2, "layernorm_fwd: bad dropout");
   if (rows == 0) return UNIVL_OK;
-  layernorm_fwd_kernel<bf16><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
-      make_drop(drop_mode, p_drop, rng_state, stream_id));
+  launch_kernel(layernorm_fwd_kernel<bf16>, dim3(ln_grid(rows)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream,
+                (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
+                make_drop(drop_mode, p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("layernorm_fwd");
   return UNIVL_OK;
 }
@@ -341,8 +345,9 @@ extern "C" int univl_layernorm_f32_fwd(const float* x, const float* gamma, const
   if (int rc = check_ln_shape("layernorm_f32_fwd", rows, cols)) return rc;
   UNIVL_CHECK_ARG(x && gamma && beta && y, "layernorm_f32_fwd: null pointer");
   if (rows == 0) return UNIVL_OK;
-  layernorm_fwd_kernel<float><<<ln_grid(rows), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps, make_drop(0, 0.f, nullptr, 0));
+  launch_kernel(layernorm_fwd_kernel<float>, dim3(ln_grid(rows)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, x,
+                (const bf16*)nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
+                make_drop(0, 0.f, nullptr, 0));
   UNIVL_CHECK_LAUNCH("layernorm_f32_fwd");
   return UNIVL_OK;
 }

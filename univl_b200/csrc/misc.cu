@@ -7,6 +7,8 @@ namespace univl {
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int rows, int cols,
                    int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][257];
   const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + cv * 8;
@@ -131,8 +133,8 @@ extern "C" int univl_colsum_bf16(const void* x, long long ld, float* out, int ro
   if (row_blocks < 1) row_blocks = 1;
   const int rpb = (rows + row_blocks - 1) / row_blocks;
   row_blocks = (rows + rpb - 1) / rpb;
-  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, rows,
-                                                                                     cols, rpb);
+  launch_kernel(colsum_bf16_kernel, dim3(col_blocks, row_blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, ld,
+                out, rows, cols, rpb);
   UNIVL_CHECK_LAUNCH("colsum_bf16");
   return UNIVL_OK;
 }
