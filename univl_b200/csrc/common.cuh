@@ -95,28 +95,43 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 
 // erf-GELU as the reference states it: x * 0.5 * (1 + erf(x / sqrt(2)))  (modules/until_module.py:28-33).
 // erf is evaluated with Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, two orders below bf16 resolution) because the
-// GEMM epilogue is instruction-bound: one MUFU.RCP + one MUFU.EX2 + 7 FMAs instead of libdevice's branchy erff.  The
-// same exponential exp(-x^2/2) serves the derivative's Gaussian term.
-__device__ __forceinline__ void erf_exp_terms(float x, float& erf_abs, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752440f;            // |x| / sqrt(2)
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  gauss = __expf(-z * z);                                        // exp(-x^2 / 2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  erf_abs = fmaf(-poly * t, gauss, 1.0f);                        // erf(|x| / sqrt(2))
+// GEMM epilogue is instruction-bound: one MUFU.RCP + one MUFU.EX2 + a handful of FMAs instead of libdevice's branchy
+// erff.  The same exponential exp(-x^2/2) serves the derivative's Gaussian term.
+// Arranged for the fewest issue slots (11 FP + 2 MUFU forward, 15 + 2 for the derivative):
+//   w(x) = 1 - Phi(|x|) = 0.5 * t * poly(t) * exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt(2))      (A&S 7.1.26)
+//   gelu(x)  = max(x, 0) - |x| * w(x)
+//   gelu'(x) = Phi(x) + x * phi(x),   Phi(x) = x >= 0 ? 1 - w : w
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// w = 1 - Phi(|x|) (in [0, 0.5]) and gauss = exp(-x^2 / 2)
+__device__ __forceinline__ void erf_exp_terms(float x, float& w, float& gauss) {
+  const float t = rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752440f, 1.0f));
+  gauss = ex2_approx((x * x) * (-0.5f * 1.44269504088896340736f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  w = (poly * t) * gauss;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float e, g;
-  erf_exp_terms(x, e, g);
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  float w, g;
+  erf_exp_terms(x, w, g);
+  return fmaf(-fabsf(x), w, fmaxf(x, 0.f));
 }
 // d/dx gelu_erf(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float e, g;
-  erf_exp_terms(x, e, g);
-  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + copysignf(e, x)));
+  float w, g;
+  erf_exp_terms(x, w, g);
+  const float cdf = x >= 0.f ? 1.0f - w : w;
+  return fmaf(x * 0.39894228040143267794f, g, cdf);
 }
 
 // ----------------------------------------------------------------------------

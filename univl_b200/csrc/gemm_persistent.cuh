@@ -241,10 +241,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ac
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_acc + (uint32_t)(c + j * 16), r);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]) * alpha;
+        for (int e = 0; e < 16; ++e) v[j * 16 + e] = __uint_as_float(r[e]);
       }
     }
     tmem_ld_wait();
+    if (alpha != 1.0f) {  // warp-uniform; the common case (alpha = 1) spends no issue slot on it
+#pragma unroll
+      for (int e = 0; e < 64; ++e) v[e] *= alpha;
+    }
     if (p.tma_epilogue) epilogue_chunk_tma(p, epi, out_f32, CH, v, row0, col, lane, st, tm_out, tm_aux);
     else epilogue_chunk_manual(p, epi, out_f32, CH, v, row0, row0 + lane, col, lane, st.stage);
   }
@@ -416,7 +420,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-    if (lane == 0) bulk_wait_all();  // outstanding bulk stores still read this CTA's shared memory
+    if (lane == 0) bulk_wait_read<0>();  // outstanding bulk stores still read this CTA's shared memory (the writes
+                                         // themselves complete asynchronously; kernel completion orders them)
   }
 
   tc_fence_before_sync();
@@ -627,7 +632,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_read<0>();
   }
 
   __syncwarp();

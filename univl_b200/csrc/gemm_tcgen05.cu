@@ -454,7 +454,9 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
   const int total_kb = (Kc + BLOCK_K - 1) / BLOCK_K;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   // tile width: widest tile that still yields >= ~1 wave of CTAs on 148 SMs
-  int bn = block_n;
+  // tuning overrides carried in block_n: +512 forces the CTA-pair kernel, +1024 forces single-CTA tiles
+  const int force_pair = (block_n & 512) ? 1 : (block_n & 1024) ? -1 : 0;
+  int bn = block_n & 511;
   if (bn == 0) {
     bn = 256;
     // without split-K the tile count alone must fill the SMs; with the atomic epilogue split-K supplies the
@@ -486,6 +488,7 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
     const long long pair_work = (long long)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * n_tiles * splits;
     pair = pair_mode() == 2 || pair_work >= 60;
   }
+  if (force_pair != 0 && !use_v1_kernel() && bn == 256) pair = force_pair > 0;
 
   CUtensorMap ta, tb;
   int rc;

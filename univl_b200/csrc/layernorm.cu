@@ -32,6 +32,31 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+// raw (still packed) 8-element vectors: what a software-pipelined row loop keeps in flight for the NEXT row
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void raw_load(const bf16* p, Raw8<bf16>& r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.u.x), "=r"(r.u.y), "=r"(r.u.z), "=r"(r.u.w) : "l"(p));
+}
+__device__ __forceinline__ void raw_load(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<bf16>& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+  v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
 __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]);
@@ -56,58 +81,75 @@ __device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
   return d;
 }
 
-// keep flags of 8 consecutive elements starting at flat index idx0 (idx0 % 8 == 0): one Philox call
-__device__ __forceinline__ void keep8(const DropCfg& d, uint64_t idx0, bool (&k)[8]) {
-  const uint32_t m = dropout_keep8(d.seed, d.stream, idx0, d.threshold);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) k[j] = (m >> j) & 1u;
+// keep bits of 8 consecutive elements starting at flat index idx0 (idx0 % 8 == 0): one Philox call
+__device__ __forceinline__ uint32_t keep8_mask(const DropCfg& d, uint64_t idx0) {
+  return dropout_keep8(d.seed, d.stream, idx0, d.threshold);
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// The row loop is software-pipelined: the raw vectors of the warp's NEXT row are requested before the current row's
+// reductions, so every warp always has a full row of loads in flight (the un-pipelined loop spent 67% of its issue
+// slots stalled on the long scoreboard: r01 ncu capture, 2.85 TB/s).
+template <typename TIn, int NVEC>
+__global__ void __launch_bounds__(LN_WARPS * 32, NVEC <= 3 ? 3 : 2)
 layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows, int cols, float eps, DropCfg drop_in) {
+                     float* __restrict__ rstd_out, int rows, float eps, DropCfg drop_in) {
   pdl_trigger();
   pdl_wait();
   const DropCfg drop = resolve_drop(drop_in);
+  constexpr int cols = NVEC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nvec = cols >> 8;
   const float inv_cols = 1.0f / (float)cols;
-  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-    float z[LN_MAX_VEC][8];
+  const long long stride = (long long)gridDim.x * LN_WARPS;
+  long long row = (long long)blockIdx.x * LN_WARPS + warp;
+  Raw8<TIn> nx[NVEC];
+  Raw8<bf16> nr[NVEC];
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const long long off = row * cols + (i * 32 + lane) * 8;
+      raw_load(x + off, nx[i]);
+      if (res != nullptr) raw_load(res + off, nr[i]);
+    }
+  }
+  for (; row < rows; row += stride) {
+    float z[NVEC][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-      if (i < nvec) {
-        const int c = (i * 32 + lane) * 8;
-        load8(x + row * cols + c, z[i]);
-        if (drop.mode == 1) {
-          bool k[8];
-          keep8(drop, (uint64_t)row * cols + c, k);
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      raw_unpack(nx[i], z[i]);
+      if (drop.mode == 1) {
+        const uint32_t keep = keep8_mask(drop, (uint64_t)row * cols + c);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[i][j] = k[j] ? z[i][j] * drop.scale : 0.f;
-        }
-        if (res != nullptr) {
-          float r[8];
-          load8(res + row * cols + c, r);
+        for (int j = 0; j < 8; ++j) z[i][j] = ((keep >> j) & 1u) ? z[i][j] * drop.scale : 0.f;
+      }
+      if (res != nullptr) {
+        float r[8];
+        raw_unpack(nr[i], r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[i][j] += r[j];
-        }
+        for (int j = 0; j < 8; ++j) z[i][j] += r[j];
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += z[i][j];
+      for (int j = 0; j < 8; ++j) s += z[i][j];
+    }
+    const long long next = row + stride;
+    if (next < rows) {
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        const long long off = next * cols + (i * 32 + lane) * 8;
+        raw_load(x + off, nx[i]);
+        if (res != nullptr) raw_load(res + off, nr[i]);
       }
     }
     const float mean = warp_sum(s) * inv_cols;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
-      if (i < nvec) {
+    for (int i = 0; i < NVEC; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = z[i][j] - mean;
-          q += d * d;
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float d = z[i][j] - mean;
+        q += d * d;
       }
     const float var = warp_sum(q) * inv_cols;
     const float rstd = 1.0f / sqrtf(var + eps);
@@ -116,22 +158,33 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, co
       if (rstd_out) rstd_out[row] = rstd;
     }
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
-      if (i < nvec) {
-        const int c = (i * 32 + lane) * 8;
-        float g[8], b[8], o[8];
-        load8(gamma + c, g);
-        load8(beta + c, b);
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float g[8], b[8], o[8];
+      load8(gamma + c, g);
+      load8(beta + c, b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = g[j] * ((z[i][j] - mean) * rstd) + b[j];
-        if (drop.mode == 2) {
-          bool k[8];
-          keep8(drop, (uint64_t)row * cols + c, k);
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * ((z[i][j] - mean) * rstd) + b[j];
+      if (drop.mode == 2) {
+        const uint32_t keep = keep8_mask(drop, (uint64_t)row * cols + c);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = k[j] ? o[j] * drop.scale : 0.f;
-        }
-        store8(y + row * cols + c, o);
+        for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * drop.scale : 0.f;
       }
+      store8(y + row * cols + c, o);
+    }
+  }
+}
+
+template <typename TIn>
+static void launch_ln_fwd(int grid, cudaStream_t st, const TIn* x, const bf16* res, const float* gamma,
+                          const float* beta, bf16* y, float* mean, float* rstd, int rows, int cols, float eps,
+                          DropCfg drop) {
+  const dim3 g(grid), b(LN_WARPS * 32);
+  switch (cols >> 8) {
+    case 1: launch_kernel(layernorm_fwd_kernel<TIn, 1>, g, b, 0, st, x, res, gamma, beta, y, mean, rstd, rows, eps, drop); break;
+    case 2: launch_kernel(layernorm_fwd_kernel<TIn, 2>, g, b, 0, st, x, res, gamma, beta, y, mean, rstd, rows, eps, drop); break;
+    case 3: launch_kernel(layernorm_fwd_kernel<TIn, 3>, g, b, 0, st, x, res, gamma, beta, y, mean, rstd, rows, eps, drop); break;
+    default: launch_kernel(layernorm_fwd_kernel<TIn, 4>, g, b, 0, st, x, res, gamma, beta, y, mean, rstd, rows, eps, drop); break;
   }
 }
 
@@ -139,9 +192,6 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, const bf16* __restrict__ res, co
 //   dx_res   (bf16, may be null): dz                       — gradient w.r.t. the residual input (and x when no dropout)
 //   dx_dense (bf16, may be null): dz * keep/(1-p)          — gradient w.r.t. x under drop_mode 1
 //   dgamma, dbeta (fp32, atomically accumulated), dbias (fp32, optional) += column sums of dx_dense (or dz)
-__device__ __forceinline__ uint32_t keep8_mask(const DropCfg& d, uint64_t idx0) {
-  return dropout_keep8(d.seed, d.stream, idx0, d.threshold);
-}
 
 // one 8-wide vector of the row: z = pre-LayerNorm value, d = effective upstream gradient, keep = dropout bit mask
 template <typename TIn>
@@ -174,12 +224,12 @@ __device__ __forceinline__ void ln_bwd_load(const bf16* dy, const bf16* dy2, con
   }
 }
 
-// Two sweeps over the row instead of holding it in registers: sweep 1 accumulates the two row statistics and the
-// dgamma/dbeta partials, sweep 2 re-reads the (L1-resident) row and emits dz.  Halving the live registers doubles the
-// resident warps per SM, which is what this latency-bound kernel needs.
+// Single sweep: the normalised row and g = dy * gamma stay in registers between the statistics and the dz phase, so each
+// element is loaded, unpacked and (under dropout) Philox-masked exactly once.  (The earlier two-sweep form re-read the
+// L1-resident row and regenerated the mask: 68 issued instructions per element, issue-bound at 2.4 TB/s.)
 constexpr int LNB_WARPS = 4;  // backward: 4-warp CTAs, <= 168 registers -> 3 CTAs (12 warps) per SM
 template <typename TIn, int NVEC>
-__global__ void __launch_bounds__(LNB_WARPS * 32, 3)
+__global__ void __launch_bounds__(LNB_WARPS * 32, NVEC <= 3 ? 3 : 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const TIn* __restrict__ x,
                      const bf16* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, bf16* __restrict__ dx_res, bf16* __restrict__ dx_dense,
@@ -192,6 +242,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
   constexpr int cols = NVEC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_cols = 1.0f / (float)cols;
+  const bool emit = dx_res != nullptr || dx_dense != nullptr || dbias != nullptr;
   float acc_g[NVEC][8], acc_b[NVEC][8], acc_x[NVEC][8];
 #pragma unroll
   for (int i = 0; i < NVEC; ++i)
@@ -200,39 +251,40 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 
   for (long long row = (long long)blockIdx.x * LNB_WARPS + warp; row < rows; row += (long long)gridDim.x * LNB_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
+    const float nm = -mean * rstd;
+    float xh[NVEC][8], g[NVEC][8];
+    uint32_t keep[NVEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = (i * 32 + lane) * 8;
-      float z[8], d[8], gm[8];
-      uint32_t keep;
-      ln_bwd_load(dy, dy2, x, res, row * cols + c, drop, z, d, keep);
+      float d[8], gm[8];
+      ln_bwd_load(dy, dy2, x, res, row * cols + c, drop, xh[i], d, keep[i]);
       load8(gamma + c, gm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (z[j] - mean) * rstd;
-        const float g = d[j] * gm[j];
-        s1 += g;
-        s2 += g * xh;
-        acc_g[i][j] += d[j] * xh;
+        const float h = fmaf(xh[i][j], rstd, nm);
+        const float gg = d[j] * gm[j];
+        s1 += gg;
+        s2 = fmaf(gg, h, s2);
+        acc_g[i][j] = fmaf(d[j], h, acc_g[i][j]);
         acc_b[i][j] += d[j];
+        xh[i][j] = h;
+        g[i][j] = gg;
       }
     }
-    s1 = warp_sum(s1) * inv_cols;
-    s2 = warp_sum(s2) * inv_cols;
-    if (dx_res == nullptr && dx_dense == nullptr && dbias == nullptr) continue;  // parameter gradients only
+    if (!emit) continue;  // parameter gradients only
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const float a = -s1 * inv_cols * rstd, b = -s2 * inv_cols * rstd;
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = (i * 32 + lane) * 8;
-      float z[8], d[8], gm[8], dz[8], dd[8];
-      uint32_t keep;
-      ln_bwd_load(dy, dy2, x, res, row * cols + c, drop, z, d, keep);
-      load8(gamma + c, gm);
+      float dz[8], dd[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (z[j] - mean) * rstd;
-        dz[j] = rstd * (d[j] * gm[j] - s1 - xh * s2);
-        dd[j] = (drop.mode == 1) ? (((keep >> j) & 1u) ? dz[j] * drop.scale : 0.f) : dz[j];
+        dz[j] = fmaf(xh[i][j], b, fmaf(g[i][j], rstd, a));
+        dd[j] = (drop.mode == 1) ? (((keep[i] >> j) & 1u) ? dz[j] * drop.scale : 0.f) : dz[j];
         acc_x[i][j] += dd[j];
       }
       if (dx_res != nullptr) store8(dx_res + row * cols + c, dz);
@@ -315,9 +367,8 @@ extern "C" int univl_layernorm_fwd(const void* x, const void* res, const float* 
   UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "layernorm_fwd: dropout needs rng_state");
   UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && drop_mode >= 0 && drop_mode <= 2, "layernorm_fwd: bad dropout");
   if (rows == 0) return UNIVL_OK;
-  launch_kernel(layernorm_fwd_kernel<bf16>, dim3(ln_grid(rows)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream,
-                (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
-                make_drop(drop_mode, p_drop, rng_state, stream_id));
+  launch_ln_fwd<bf16>(ln_grid(rows), (cudaStream_t)stream, (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, mean,
+                      rstd, rows, cols, eps, make_drop(drop_mode, p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("layernorm_fwd");
   return UNIVL_OK;
 }
@@ -345,9 +396,8 @@ extern "C" int univl_layernorm_f32_fwd(const float* x, const float* gamma, const
   if (int rc = check_ln_shape("layernorm_f32_fwd", rows, cols)) return rc;
   UNIVL_CHECK_ARG(x && gamma && beta && y, "layernorm_f32_fwd: null pointer");
   if (rows == 0) return UNIVL_OK;
-  launch_kernel(layernorm_fwd_kernel<float>, dim3(ln_grid(rows)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, x,
-                (const bf16*)nullptr, gamma, beta, (bf16*)y, mean, rstd, rows, cols, eps,
-                make_drop(0, 0.f, nullptr, 0));
+  launch_ln_fwd<float>(ln_grid(rows), (cudaStream_t)stream, x, (const bf16*)nullptr, gamma, beta, (bf16*)y, mean, rstd,
+                       rows, cols, eps, make_drop(0, 0.f, nullptr, 0));
   UNIVL_CHECK_LAUNCH("layernorm_f32_fwd");
   return UNIVL_OK;
 }

@@ -3,6 +3,13 @@
 
 namespace univl {
 
+__device__ __forceinline__ uint4 ld_nc_v4(const bf16* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
+
 // out[c] += sum_r x[r, c]   (bf16 in, fp32 atomic accumulate).  Block = 32 column-vectors (256 cols) x 8 row lanes.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int rows, int cols,
@@ -17,19 +24,31 @@ colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  if (c0 < cols) {
-    for (int r = r_begin + rl; r < r_end; r += 8) {
-      const bf16* p = x + (long long)r * ld + c0;
-      if (c0 + 8 <= cols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  auto add8 = [&](const uint4& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
-          acc[2 * j] += f.x;
-          acc[2 * j + 1] += f.y;
-        }
-      } else {
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  };
+  if (c0 < cols) {
+    const bf16* base = x + c0;
+    if (c0 + 8 <= cols && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+      // four independent 16-byte loads in flight per thread (the one-load loop was 85% long-scoreboard stalls)
+      int r = r_begin + rl;
+      for (; r + 24 < r_end; r += 32) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = ld_nc_v4(base + (long long)(r + 8 * k) * ld);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) add8(u[k]);
+      }
+      for (; r < r_end; r += 8) add8(ld_nc_v4(base + (long long)r * ld));
+    } else {
+      for (int r = r_begin + rl; r < r_end; r += 8) {
+        const bf16* p = base + (long long)r * ld;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (c0 + j < cols) acc[j] += __bfloat162float(p[j]);
