@@ -149,9 +149,47 @@ __device__ __forceinline__ void flush_colsums(float (&acc)[EMB_VEC][8], float* d
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < EMB_WARPS; ++w) t += red[w][e];
-      atomicAdd(dst + i * 256 + e, t);
+      if (t != 0.f) atomicAdd(dst + i * 256 + e, t);
     }
   }
+}
+
+// Table-gradient accumulation.  Hundreds of token rows share one position row and practically all share one type row,
+// so per-element atomics serialise in L2 (measured: the two embedding backward kernels spent most of their 0.5 ms
+// there).  Each warp instead walks rows whose position index is constant (the row stride is a multiple of the sequence
+// length), keeps the position / type sums in registers and flushes when the key changes or at the end.
+struct KeyedAcc {
+  float v[EMB_VEC][8];
+  int key;
+};
+__device__ __forceinline__ void keyed_init(KeyedAcc& a) {
+  a.key = -1;
+#pragma unroll
+  for (int i = 0; i < EMB_VEC; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[i][j] = 0.f;
+}
+__device__ __forceinline__ void keyed_flush(KeyedAcc& a, float* table, int lane) {
+  if (a.key < 0) return;
+#pragma unroll
+  for (int i = 0; i < EMB_VEC; ++i) {
+    float* dst = table + (long long)a.key * EMB_H + (i * 32 + lane) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dst + j, a.v[i][j]);
+      a.v[i][j] = 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void keyed_add(KeyedAcc& a, int key, const float (&dz)[8], int i) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a.v[i][j] += dz[j];
+  a.key = key;
+}
+// rows [0, n_rows) are walked as  first + k * stride  with stride = the largest multiple of `period` that the launched
+// warps cover, so a warp's position index (row % period) never changes; surplus warps idle
+__device__ __forceinline__ long long period_stride(long long launched_warps, int period) {
+  return launched_warps >= period ? (launched_warps / period) * period : launched_warps;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -207,7 +245,13 @@ embed_text_bwd_kernel(const bf16* __restrict__ dy, const long long* __restrict__
   for (int i = 0; i < EMB_VEC; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = 0.f;
-  for (long long row = (long long)blockIdx.x * EMB_WARPS + warp; row < rows; row += (long long)gridDim.x * EMB_WARPS) {
+  KeyedAcc acc_p, acc_t;
+  keyed_init(acc_p);
+  keyed_init(acc_t);
+  const long long stride = period_stride((long long)gridDim.x * EMB_WARPS, S);
+  long long row = (long long)blockIdx.x * EMB_WARPS + warp;
+  if (row >= stride) row = rows;
+  for (; row < rows; row += stride) {
     const int s = (int)(row % S);
     long long id = ids[row];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -229,15 +273,27 @@ embed_text_bwd_kernel(const bf16* __restrict__ dy, const long long* __restrict__
       }
     }
     ln_row_bwd(z, dy + row * EMB_H, gamma, mean_in[row], rstd_in[row], row, drop, lane, dz, acc_g, acc_b);
+    if (acc_p.key != s) keyed_flush(acc_p, dpos, lane);
+    if (dtype != nullptr && acc_t.key != (int)t) keyed_flush(acc_t, dtype, lane);
 #pragma unroll
     for (int i = 0; i < EMB_VEC; ++i) {
       const int c = (i * 32 + lane) * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(dword + id * EMB_H + c + j, dz[i][j]);
-        atomicAdd(dpos + (long long)s * EMB_H + c + j, dz[i][j]);
-        if (dtype != nullptr) atomicAdd(dtype + t * EMB_H + c + j, dz[i][j]);
-      }
+      for (int j = 0; j < 8; ++j) atomicAdd(dword + id * EMB_H + c + j, dz[i][j]);
+      keyed_add(acc_p, s, dz[i], i);
+      if (dtype != nullptr) keyed_add(acc_t, (int)t, dz[i], i);
+    }
+  }
+  keyed_flush(acc_p, dpos, lane);
+  if (dtype != nullptr) {
+    // type sums: reduce over the CTA's warps first (one atomic per column per CTA and type row)
+    for (int tt = 0; tt < 2; ++tt) {
+      float part[EMB_VEC][8];
+#pragma unroll
+      for (int i = 0; i < EMB_VEC; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[i][j] = acc_t.key == tt ? acc_t.v[i][j] : 0.f;
+      flush_colsums(part, dtype + tt * EMB_H, red, warp, lane);
     }
   }
   flush_colsums(acc_g, dgamma, red, warp, lane);
@@ -254,48 +310,108 @@ struct SrcCfg {
   int all_pairs;  // 0: sequence p reads (a[p], b[p]); 1: p = i * Nb + j reads (a[i], b[j])
 };
 
-__device__ __forceinline__ const bf16* src_row(const SrcCfg& c, long long p, int s) {
-  const long long i = c.all_pairs ? p / c.Nb : p;
-  const long long j = c.all_pairs ? p % c.Nb : p;
-  return s < c.Wa ? c.a + (i * c.Wa + s) * EMB_H : c.b + (j * c.Fb + (s - c.Wa)) * EMB_H;
+// Shared by both source kernels: one warp owns one SOURCE row (text row of a, or video row of b; blockIdx.y selects).
+// Every output sequence that reads this row (1 in aligned mode; Nb or Na in all-pairs mode) sees the SAME pre-LN
+// vector z = src + pos (+ type), hence the same mean / rstd / normalised row: LayerNorm runs once per source row and
+// only the dropout mask differs between the fan-out rows.
+struct SrcRow {
+  long long owner;  // i (text) or j (video)
+  int s;            // position inside the concatenated sequence
+  int fan;          // number of output sequences reading this row
+};
+__device__ __forceinline__ SrcRow src_row_info(const SrcCfg& c, int which, long long sr) {
+  const int len = which == 0 ? c.Wa : c.Fb;
+  SrcRow r;
+  r.owner = sr / len;
+  r.s = (int)(sr % len) + (which == 0 ? 0 : c.Wa);
+  r.fan = c.all_pairs ? (which == 0 ? c.Nb : c.Na) : 1;
+  return r;
+}
+__device__ __forceinline__ long long src_out_row(const SrcCfg& c, int which, const SrcRow& r, int f) {
+  const long long p = c.all_pairs ? (which == 0 ? r.owner * c.Nb + f : (long long)f * c.Nb + r.owner) : r.owner;
+  return p * (c.Wa + c.Fb) + r.s;
+}
+__device__ __forceinline__ void src_load_z(const SrcCfg& c, int which, long long sr, const SrcRow& r,
+                                           const float* pos, const float* type, int lane, float (&z)[EMB_VEC][8]) {
+  const bf16* xr = (which == 0 ? c.a : c.b) + sr * EMB_H;
+#pragma unroll
+  for (int i = 0; i < EMB_VEC; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    float a[8], b[8];
+    ld8h(xr + col, a);
+    ld8f(pos + (long long)r.s * EMB_H + col, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[i][j] = a[j] + b[j];
+    if (type != nullptr) {
+      float tt[8];
+      ld8f(type + (which == 0 ? 0 : EMB_H) + col, tt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[i][j] += tt[j];
+    }
+  }
 }
 
 __global__ void __launch_bounds__(EMB_WARPS * 32)
 embed_src_fwd_kernel(SrcCfg src, const float* __restrict__ pos, const float* __restrict__ type,
                      const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y,
-                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long n_seq, float eps,
-                     EmbDrop drop_in) {
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, float eps, EmbDrop drop_in) {
   const EmbDrop drop = resolve_emb_drop(drop_in);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = src.Wa + src.Fb;
-  const long long rows = n_seq * S;
-  for (long long row = (long long)blockIdx.x * EMB_WARPS + warp; row < rows; row += (long long)gridDim.x * EMB_WARPS) {
-    const long long p = row / S;
-    const int s = (int)(row % S);
-    const bf16* xr = src_row(src, p, s);
+  const int which = blockIdx.y;
+  const long long n_src_rows = which == 0 ? (long long)src.Na * src.Wa : (long long)src.Nb * src.Fb;
+  for (long long sr = (long long)blockIdx.x * EMB_WARPS + warp; sr < n_src_rows;
+       sr += (long long)gridDim.x * EMB_WARPS) {
+    const SrcRow r = src_row_info(src, which, sr);
     float z[EMB_VEC][8];
+    src_load_z(src, which, sr, r, pos, type, lane, z);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < EMB_VEC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += z[i][j];
+    const float mean = warp_sum(sum) * (1.0f / EMB_H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < EMB_VEC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = z[i][j] - mean;
+        q += d * d;
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / EMB_H) + eps);
 #pragma unroll
     for (int i = 0; i < EMB_VEC; ++i) {
-      const int c = (i * 32 + lane) * 8;
-      float a[8], b[8];
-      ld8h(xr + c, a);
-      ld8f(pos + (long long)s * EMB_H + c, b);
+      const int col = (i * 32 + lane) * 8;
+      float g[8], b[8];
+      ld8f(gamma + col, g);
+      ld8f(beta + col, b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[i][j] = a[j] + b[j];
-      if (type != nullptr) {
-        float tt[8];
-        ld8f(type + (s < src.Wa ? 0 : EMB_H) + c, tt);
+      for (int j = 0; j < 8; ++j) z[i][j] = g[j] * ((z[i][j] - mean) * rstd) + b[j];
+    }
+    for (int f = 0; f < r.fan; ++f) {
+      const long long row = src_out_row(src, which, r, f);
+      if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[i][j] += tt[j];
+      for (int i = 0; i < EMB_VEC; ++i) {
+        const int col = (i * 32 + lane) * 8;
+        float o[8];
+        uint32_t keep = 0xffu;
+        if (drop.on) keep = dropout_keep8(drop.seed, drop.stream, (uint64_t)row * EMB_H + col, drop.threshold);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? z[i][j] * drop.scale : 0.f;
+        st8h(y + row * EMB_H + col, o);
       }
     }
-    ln_row_fwd(z, gamma, beta, y + row * EMB_H, mean_out, rstd_out, row, eps, drop, lane);
   }
 }
 
-// One warp per SOURCE row: it walks every output sequence that read this row (1 in aligned mode, Nb or Na in
-// all-pairs mode), sums dz in registers and writes the source gradient once — deterministic, no atomics on
-// activations.  blockIdx.y selects the source (0 = a, 1 = b).
+// Backward: LayerNorm backward is linear in the upstream gradient and z / mean / rstd are shared by the fan-out rows,
+// so the (dropout-masked) dy rows are first SUMMED over the fan-out — SRC_BATCH rows of 16-byte loads in flight per lane —
+// and one LayerNorm backward runs on the sum.  Deterministic, no atomics on activations.
+constexpr int SRC_BATCH = 2;
 __global__ void __launch_bounds__(EMB_WARPS * 32)
 embed_src_bwd_kernel(const bf16* __restrict__ dy, SrcCfg src, const float* __restrict__ pos,
                      const float* __restrict__ type, const float* __restrict__ gamma,
@@ -305,7 +421,6 @@ embed_src_bwd_kernel(const bf16* __restrict__ dy, SrcCfg src, const float* __res
   const EmbDrop drop = resolve_emb_drop(drop_in);
   __shared__ float red[EMB_WARPS][257];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = src.Wa + src.Fb;
   const int which = blockIdx.y;  // 0: rows of a, 1: rows of b
   const long long n_src_rows = which == 0 ? (long long)src.Na * src.Wa : (long long)src.Nb * src.Fb;
   float acc_g[EMB_VEC][8], acc_b[EMB_VEC][8];
@@ -313,54 +428,97 @@ embed_src_bwd_kernel(const bf16* __restrict__ dy, SrcCfg src, const float* __res
   for (int i = 0; i < EMB_VEC; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = 0.f;
-  for (long long sr = (long long)blockIdx.x * EMB_WARPS + warp; sr < n_src_rows;
-       sr += (long long)gridDim.x * EMB_WARPS) {
-    const int len = which == 0 ? src.Wa : src.Fb;
-    const long long owner = sr / len;           // i (text) or j (video)
-    const int s = (int)(sr % len) + (which == 0 ? 0 : src.Wa);
-    const bf16* xr = (which == 0 ? src.a : src.b) + sr * EMB_H;
-    float z[EMB_VEC][8], sum[EMB_VEC][8];
+  KeyedAcc acc_p;
+  keyed_init(acc_p);
+  float acc_t[EMB_VEC][8];
 #pragma unroll
-    for (int i = 0; i < EMB_VEC; ++i) {
-      const int c = (i * 32 + lane) * 8;
-      float a[8], b[8];
-      ld8h(xr + c, a);
-      ld8f(pos + (long long)s * EMB_H + c, b);
+  for (int i = 0; i < EMB_VEC; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        z[i][j] = a[j] + b[j];
-        sum[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc_t[i][j] = 0.f;
+  const long long stride = period_stride((long long)gridDim.x * EMB_WARPS, which == 0 ? src.Wa : src.Fb);
+  long long sr = (long long)blockIdx.x * EMB_WARPS + warp;
+  if (sr >= stride) sr = n_src_rows;
+  for (; sr < n_src_rows; sr += stride) {
+    const SrcRow r = src_row_info(src, which, sr);
+    float D[EMB_VEC][8];
+#pragma unroll
+    for (int i = 0; i < EMB_VEC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) D[i][j] = 0.f;
+    for (int f0 = 0; f0 < r.fan; f0 += SRC_BATCH) {
+      uint4 raw[SRC_BATCH][EMB_VEC];
+      long long rows[SRC_BATCH];
+#pragma unroll
+      for (int u = 0; u < SRC_BATCH; ++u) {
+        rows[u] = src_out_row(src, which, r, min(f0 + u, r.fan - 1));
+#pragma unroll
+        for (int i = 0; i < EMB_VEC; ++i)
+          raw[u][i] = *reinterpret_cast<const uint4*>(dy + rows[u] * EMB_H + (i * 32 + lane) * 8);
       }
-      if (type != nullptr) {
-        float tt[8];
-        ld8f(type + (which == 0 ? 0 : EMB_H) + c, tt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[i][j] += tt[j];
+      for (int u = 0; u < SRC_BATCH; ++u) {
+        if (f0 + u >= r.fan) continue;
+#pragma unroll
+        for (int i = 0; i < EMB_VEC; ++i) {
+          const int col = (i * 32 + lane) * 8;
+          uint32_t keep = 0xffu;
+          if (drop.on) keep = dropout_keep8(drop.seed, drop.stream, (uint64_t)rows[u] * EMB_H + col, drop.threshold);
+          const uint32_t w[4] = {raw[u][i].x, raw[u][i].y, raw[u][i].z, raw[u][i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 v = unpack_bf16x2(w[j]);
+            if ((keep >> (2 * j)) & 1u) D[i][2 * j] += v.x;
+            if ((keep >> (2 * j + 1)) & 1u) D[i][2 * j + 1] += v.y;
+          }
+        }
       }
     }
-    const int fan = src.all_pairs ? (which == 0 ? src.Nb : src.Na) : 1;
-    for (int f = 0; f < fan; ++f) {
-      const long long p = src.all_pairs ? (which == 0 ? owner * src.Nb + f : (long long)f * src.Nb + owner) : owner;
-      const long long row = p * S + s;
-      float dz[EMB_VEC][8];
-      ln_row_bwd(z, dy + row * EMB_H, gamma, mean_in[row], rstd_in[row], row, drop, lane, dz, acc_g, acc_b);
+    if (drop.on) {
 #pragma unroll
       for (int i = 0; i < EMB_VEC; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum[i][j] += dz[i][j];
+        for (int j = 0; j < 8; ++j) D[i][j] *= drop.scale;
     }
-    bf16* dst = (which == 0 ? da : db);
+    // one LayerNorm backward on the summed gradient
+    const long long row0 = src_out_row(src, which, r, 0);
+    const float mean = mean_in[row0], rstd = rstd_in[row0];
+    float z[EMB_VEC][8];
+    src_load_z(src, which, sr, r, pos, type, lane, z);
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < EMB_VEC; ++i) {
-      const int c = (i * 32 + lane) * 8;
-      if (dst != nullptr) st8h(dst + sr * EMB_H + c, sum[i]);
+      float gm[8];
+      ld8f(gamma + (i * 32 + lane) * 8, gm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dpos + (long long)s * EMB_H + c + j, sum[i][j]);
-        if (dtype != nullptr) atomicAdd(dtype + (which == 0 ? 0 : EMB_H) + c + j, sum[i][j]);
+        const float xh = (z[i][j] - mean) * rstd;
+        const float g = D[i][j] * gm[j];
+        s1 += g;
+        s2 = fmaf(g, xh, s2);
+        acc_g[i][j] = fmaf(D[i][j], xh, acc_g[i][j]);
+        acc_b[i][j] += D[i][j];
+        z[i][j] = xh;
+        D[i][j] = g;
       }
     }
+    s1 = warp_sum(s1) * (1.0f / EMB_H);
+    s2 = warp_sum(s2) * (1.0f / EMB_H);
+    bf16* dst = (which == 0 ? da : db);
+    if (acc_p.key != r.s) keyed_flush(acc_p, dpos, lane);
+#pragma unroll
+    for (int i = 0; i < EMB_VEC; ++i) {
+      const int col = (i * 32 + lane) * 8;
+      float dz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = rstd * (D[i][j] - s1 - z[i][j] * s2);
+      if (dst != nullptr) st8h(dst + sr * EMB_H + col, dz);
+      keyed_add(acc_p, r.s, dz, i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_t[i][j] += dz[j];
+    }
   }
+  keyed_flush(acc_p, dpos, lane);
+  if (dtype != nullptr) flush_colsums(acc_t, dtype + (which == 0 ? 0 : EMB_H), red, warp, lane);
   flush_colsums(acc_g, dgamma, red, warp, lane);
   flush_colsums(acc_b, dbeta, red, warp, lane);
 }
@@ -374,6 +532,13 @@ static EmbDrop make_emb_drop(float p, const unsigned long long* rng, unsigned lo
   d.stream = stream;
   d.rng = rng;
   return d;
+}
+// backward kernels: ~2 rows per warp so the register-held table sums amortise their flush (4 rows per warp left the
+// all-pairs source kernel with 5 warps per SM: 127 us, latency-bound)
+static int emb_bwd_grid(long long rows) {
+  long long blocks = (rows + EMB_WARPS * 2 - 1) / (EMB_WARPS * 2);
+  const long long cap = 148LL * 4;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 static int emb_grid(long long rows) {
   long long blocks = (rows + EMB_WARPS - 1) / EMB_WARPS;
@@ -410,7 +575,7 @@ extern "C" int univl_embed_text_bwd(const void* dy, const long long* ids, const 
   UNIVL_CHECK_ARG(dy && ids && word && pos && gamma && mean && rstd && dword && dpos && dgamma && dbeta,
                   "embed_text_bwd: null pointer");
   if (n_seq == 0) return UNIVL_OK;
-  embed_text_bwd_kernel<<<emb_grid((long long)n_seq * S), EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  embed_text_bwd_kernel<<<emb_bwd_grid((long long)n_seq * S), EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, ids, type_ids, word, pos, type, gamma, mean, rstd, dword, dpos, dtype, dgamma, dbeta, n_seq, S,
       vocab, make_emb_drop(p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("embed_text_bwd");
@@ -428,8 +593,10 @@ extern "C" int univl_embed_src_fwd(const void* a, const void* b, const float* po
   SrcCfg src{(const bf16*)a, (const bf16*)b, Na, Wa, Fb == 0 ? 1 : Nb, Fb, all_pairs && Fb > 0};
   const long long n_seq = src.all_pairs ? (long long)Na * Nb : Na;
   if (n_seq == 0) return UNIVL_OK;
-  embed_src_fwd_kernel<<<emb_grid(n_seq * (Wa + Fb)), EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      src, pos, type, gamma, beta, (bf16*)y, mean, rstd, n_seq, eps, make_emb_drop(p_drop, rng_state, stream_id));
+  const long long rows_a = (long long)Na * Wa, rows_b = (long long)(Fb == 0 ? 0 : Nb) * Fb;
+  dim3 grid(emb_grid(rows_a > rows_b ? rows_a : rows_b), Fb == 0 ? 1 : 2);
+  embed_src_fwd_kernel<<<grid, EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      src, pos, type, gamma, beta, (bf16*)y, mean, rstd, eps, make_emb_drop(p_drop, rng_state, stream_id));
   UNIVL_CHECK_LAUNCH("embed_src_fwd");
   return UNIVL_OK;
 }
@@ -445,7 +612,7 @@ extern "C" int univl_embed_src_bwd(const void* dy, const void* a, const void* b,
   SrcCfg src{(const bf16*)a, (const bf16*)b, Na, Wa, Fb == 0 ? 1 : Nb, Fb, all_pairs && Fb > 0};
   if (Na == 0) return UNIVL_OK;
   const long long rows_a = (long long)Na * Wa, rows_b = (long long)(Fb == 0 ? 0 : Nb) * Fb;
-  dim3 grid(emb_grid(rows_a > rows_b ? rows_a : rows_b), Fb == 0 ? 1 : 2);
+  dim3 grid(emb_bwd_grid(rows_a > rows_b ? rows_a : rows_b), Fb == 0 ? 1 : 2);
   embed_src_bwd_kernel<<<grid, EMB_WARPS * 32, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, src, pos, type, gamma, mean, rstd, (bf16*)da, (bf16*)db, dpos, dtype, dgamma, dbeta,
       make_emb_drop(p_drop, rng_state, stream_id));
