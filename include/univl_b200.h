@@ -90,7 +90,7 @@ int univl_attention_bwd(const void* q, long long ldq, const void* k, long long l
                         long long lddq, void* dk, long long lddk, void* dv, long long lddv, const long long* mask_a,
                         const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq, int heads, int Sq,
                         int Sk, int causal, float scale, float p_drop, const unsigned long long* rng_state,
-                        unsigned long long stream_id, void* stream);
+                        unsigned long long stream_id, float* dbq, float* dbk, float* dbv, void* stream);
 
 /* ---- utilities ------------------------------------------------------------------------------------------------ */
 int univl_colsum_bf16(const void* x, long long ld, float* out, int rows, int cols, void* stream); /* bias grads */

@@ -167,13 +167,25 @@ def test_attention_fwd_bwd(n_seq, Sq, Sk, causal):
     ref2d.backward(d_o.float())
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
-    ops.attention_bwd(q, k, v, o, lse, d_o, dq, dkv[:, :H], dkv[:, H:], n_seq, Sq, Sk, spec)
+    dbias = torch.ones(3, H, device=DEV)  # accumulated into: starts at 1
+    ops.attention_bwd(q, k, v, o, lse, d_o, dq, dkv[:, :H], dkv[:, H:], n_seq, Sq, Sk, spec,
+                      dbias=(dbias[0], dbias[1], dbias[2]))
 
     def unheads(t, S):
         return t.permute(0, 2, 1, 3).reshape(n_seq * S, H)
-    for got, want, S in ((dq, qf.grad, Sq), (dkv[:, :H], kf.grad, Sk), (dkv[:, H:], vf.grad, Sk)):
+    for n, (got, want, S) in enumerate(((dq, qf.grad, Sq), (dkv[:, :H], kf.grad, Sk), (dkv[:, H:], vf.grad, Sk))):
         want = unheads(want, S)
         assert (got.float() - want).abs().max() <= 4e-2 * max(1.0, float(want.abs().max()))
+        # fused projection-bias gradient = column sums of the same gradient (fp32 accumulators, before the bf16
+        # rounding of the stored tile): equal to the column sums of what was stored up to that rounding, 2^-9 per
+        # element.  (The sums themselves may cancel to ~0 — dK columns do, exactly, in exact arithmetic — so the bound
+        # is relative to the summed magnitudes, not to the sum.)
+        tol = got.float().abs().sum(0) * 2.0 ** -8 + 1e-3
+        assert bool(((dbias[n] - 1.0 - got.float().sum(0)).abs() <= tol).all())
+    # the same launch without the bias pointers leaves everything else unchanged
+    dq2, dkv2 = torch.empty_like(q), torch.empty_like(kv)
+    ops.attention_bwd(q, k, v, o, lse, d_o, dq2, dkv2[:, :H], dkv2[:, H:], n_seq, Sq, Sk, spec)
+    assert torch.equal(dq2, dq) and torch.equal(dkv2, dkv)
 
 
 def test_attention_all_pairs_mask_indexing():

@@ -12,6 +12,8 @@
 // dK/dV pass of backward) at a time.  Backward recomputes P from Q, K and the saved log-sum-exp, flash-style, with
 // no atomics: dQ is produced by query-row tasks, dK/dV by key-row tasks that recompute the transposed tiles.
 // Dropout masks are Philox(seed, stream, element) and regenerated identically in every pass.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace univl {
@@ -43,6 +45,7 @@ struct AttnParams {
   bf16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
   int share_tiles;  // backward: 1 = query-major pass shares P_drop / dS with the key-major pass through smem
+  float *dbq, *dbk, *dbv;  // backward, optional: projection-bias gradients += column sums of dq / dk / dv  [heads*64]
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -373,8 +376,27 @@ struct BwdSmem {
   const float *madd, *sLse, *sD;
   bf16 *sP, *sdS;  // SHARE mode: dropped probabilities / dS, [Sq16][ldp]
   int ldp;
+  float* csum;     // per-task column sums of dq [nQ][64], dk [nK][64], dv [nK][64] (bias gradients), or null
+  int nQ, nK;
 };
 
+// column sums of a 16 x 64 accumulator tile (rows g / g+8 of the fragment layout) into this task's own 64-float slot:
+// butterfly over the 8 row groups (every lane ends up with the totals), then row group nb stores column block nb.  No
+// atomics: the slots are summed over the tasks at the end of the kernel.  (Shared-memory float atomics from four lanes
+// per warp cost 5.8 us per CTA: measured 893 vs 653 us on the cross-encoder shape.)
+__device__ __forceinline__ void tile_colsum(const float (&acc)[8][4], float* slot, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    float c0 = acc[nb][0] + acc[nb][2], c1 = acc[nb][1] + acc[nb][3];
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, m);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, m);
+    }
+    if (g == nb) *reinterpret_cast<float2*>(slot + nb * 8 + 2 * t) = make_float2(c0, c1);
+  }
+}
 template <bool SHARE>
 __device__ __forceinline__ void bwd_dq_task(const AttnParams& p, const BwdSmem& sm, int task, int lane, int seq, int h,
                                             long long bh, int Sq16, int Sk16) {
@@ -445,6 +467,7 @@ __device__ __forceinline__ void bwd_dq_task(const AttnParams& p, const BwdSmem& 
     pa[3] = pack_bf16x2(s[1][2], s[1][3]);
     mma_p_z(pa, sK, j0, lane, acc);
   }
+  if (sm.csum != nullptr) tile_colsum(acc, sm.csum + task * 64, lane);
   bf16* r0 = p.dq + ((long long)seq * p.Sq + i0) * p.lddq + h * HD;
   bf16* r1 = p.dq + ((long long)seq * p.Sq + i1) * p.lddq + h * HD;
 #pragma unroll
@@ -523,6 +546,10 @@ __device__ __forceinline__ void bwd_dkdv_task_recompute(const AttnParams& p, con
     mma_p_z(pa, sdO, q0, lane, dv);
     mma_p_z(sa, sQ, q0, lane, dk);
   }
+  if (sm.csum != nullptr) {
+    tile_colsum(dk, sm.csum + (sm.nQ + task) * 64, lane);
+    tile_colsum(dv, sm.csum + (sm.nQ + sm.nK + task) * 64, lane);
+  }
   bf16* kr0 = p.dk + ((long long)seq * p.Sk + j0r) * p.lddk + h * HD;
   bf16* kr1 = p.dk + ((long long)seq * p.Sk + j1r) * p.lddk + h * HD;
   bf16* vr0 = p.dv + ((long long)seq * p.Sk + j0r) * p.lddv + h * HD;
@@ -562,6 +589,10 @@ __device__ __forceinline__ void bwd_dkdv_task_shared(const AttnParams& p, const 
     mma_p_z(sa, sm.sQ, q0, lane, dk);
   }
   const int j0r = k0 + g, j1r = k0 + g + 8;
+  if (sm.csum != nullptr) {
+    tile_colsum(dk, sm.csum + (sm.nQ + task) * 64, lane);
+    tile_colsum(dv, sm.csum + (sm.nQ + sm.nK + task) * 64, lane);
+  }
   bf16* kr0 = p.dk + ((long long)seq * p.Sk + j0r) * p.lddk + h * HD;
   bf16* kr1 = p.dk + ((long long)seq * p.Sk + j1r) * p.lddk + h * HD;
   bf16* vr0 = p.dv + ((long long)seq * p.Sk + j0r) * p.lddv + h * HD;
@@ -600,6 +631,7 @@ attention_bwd_kernel(const AttnParams p_in) {
   float* madd = reinterpret_cast<float*>(sV + Sk16 * LDS);
   float* sLse = madd + Sk16;
   float* sD = sLse + Sq16;
+  float* csum = sD + Sq16;  // [Sq16/16 + 2 * Sk16/16][64]
 
   const int seq = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const long long bh = blockIdx.x;
@@ -639,10 +671,10 @@ attention_bwd_kernel(const AttnParams p_in) {
 
   const int nQ = Sq16 >> 4, nK = Sk16 >> 4;
   const int nw = (int)(blockDim.x >> 5);
-  BwdSmem sm{sQ, sdO, sK, sV, madd, sLse, sD, nullptr, nullptr, Sk16 + 8};
+  BwdSmem sm{sQ, sdO, sK, sV, madd, sLse, sD, nullptr, nullptr, Sk16 + 8, p.dbq != nullptr ? csum : nullptr, nQ, nK};
   if (p.share_tiles) {
     // S <= 128: the query-major pass leaves P_drop and dS in shared memory; the key-major pass only multiplies
-    sm.sP = reinterpret_cast<bf16*>(sD + Sq16);
+    sm.sP = reinterpret_cast<bf16*>(csum + (nQ + 2 * nK) * 64);
     sm.sdS = sm.sP + Sq16 * sm.ldp;
     for (int task = warp; task < nQ; task += nw) bwd_dq_task<true>(p, sm, task, lane, seq, h, bh, Sq16, Sk16);
     __syncthreads();
@@ -651,6 +683,18 @@ attention_bwd_kernel(const AttnParams p_in) {
     for (int task = warp; task < nQ + nK; task += nw) {
       if (task < nQ) bwd_dq_task<false>(p, sm, task, lane, seq, h, bh, Sq16, Sk16);
       else bwd_dkdv_task_recompute(p, sm, task - nQ, lane, seq, h, bh, Sq16, Sk16);
+    }
+  }
+  if (p.dbq != nullptr) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 192; e += blockDim.x) {
+      const int kind = e >> 6, col = e & 63;
+      const float* src = csum + (kind == 0 ? 0 : kind == 1 ? nQ : nQ + nK) * 64 + col;
+      const int n = kind == 0 ? nQ : nK;
+      float v = 0.f;
+      for (int k = 0; k < n; ++k) v += src[k * 64];
+      float* dst = kind == 0 ? p.dbq : kind == 1 ? p.dbk : p.dbv;
+      if (v != 0.f) atomicAdd(dst + h * HD + col, v);
     }
   }
 }
@@ -708,7 +752,19 @@ extern "C" int univl_attention_fwd(const void* q, long long ldq, const void* k, 
                                    : nkb <= 8 ? attention_fwd_kernel<8> : attention_fwd_kernel<0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_fwd smem attribute: %s", cudaGetErrorString(e));
-  const int fwd_warps = (Sq16 / 16) < ATT_FWD_WARPS ? (Sq16 / 16) : ATT_FWD_WARPS;
+  // warps per CTA: one per 16-row task up to 3, else two tasks per warp — smaller CTAs, more of them resident per SM, so
+  // the load phase of one overlaps the math of the others (S = 96: 3-warp CTAs measured +0.8% on the whole step)
+  const int fwd_tasks = Sq16 / 16;
+  int fwd_warps = fwd_tasks <= 3 ? fwd_tasks : (fwd_tasks + 1) / 2;
+  if (fwd_warps > ATT_FWD_WARPS) fwd_warps = ATT_FWD_WARPS;
+  {
+    static int cap = -1;  // tuning: UNIVL_ATT_FWD_WARPS=n caps the warps per CTA (more, smaller CTAs per SM)
+    if (cap < 0) {
+      const char* e = getenv("UNIVL_ATT_FWD_WARPS");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap > 0 && fwd_warps > cap) fwd_warps = cap;
+  }
   launch_kernel(kern, dim3(n_seq * heads), dim3(fwd_warps * 32), smem, (cudaStream_t)stream, p);
   UNIVL_CHECK_LAUNCH("attention_fwd");
   return UNIVL_OK;
@@ -720,7 +776,7 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
                                    long long lddv, const long long* mask_a, const long long* mask_b, int Wa, int Fb,
                                    int Nb, int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale,
                                    float p_drop, const unsigned long long* rng_state, unsigned long long stream_id,
-                                   void* stream) {
+                                   float* dbq, float* dbk, float* dbv, void* stream) {
   AttnParams p = {};
   if (int rc = fill_common(p, q, ldq, k, ldk, v, ldv, mask_a, mask_b, Wa, Fb, Nb, all_pairs, n_seq, heads, Sq, Sk,
                            causal, scale, p_drop, rng_state, stream_id))
@@ -733,8 +789,11 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
   p.d_o = (const bf16*)d_o; p.lddo = lddo;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  UNIVL_CHECK_ARG((dbq == nullptr) == (dbk == nullptr) && (dbq == nullptr) == (dbv == nullptr),
+                  "attention_bwd: bias-gradient pointers must be all set or all null");
+  p.dbq = dbq; p.dbk = dbk; p.dbv = dbv;
   const int Sq16 = (Sq + 15) & ~15, Sk16 = (Sk + 15) & ~15;
-  size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16) * 4;
+  size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16 + (Sq16 / 16 + 2 * (Sk16 / 16)) * 64) * 4;
   p.share_tiles = (Sq16 <= 128 && Sk16 <= 128) ? 1 : 0;
   if (p.share_tiles) smem += (size_t)2 * Sq16 * (Sk16 + 8) * 2;
   cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -227,9 +227,19 @@ __device__ __forceinline__ void ln_bwd_load(const bf16* dy, const bf16* dy2, con
 // Single sweep: the normalised row and g = dy * gamma stay in registers between the statistics and the dz phase, so each
 // element is loaded, unpacked and (under dropout) Philox-masked exactly once.  (The earlier two-sweep form re-read the
 // L1-resident row and regenerated the mask: 68 issued instructions per element, issue-bound at 2.4 TB/s.)
-constexpr int LNB_WARPS = 4;  // backward: 4-warp CTAs, <= 168 registers -> 3 CTAs (12 warps) per SM
+// The three column-sum accumulators (dgamma, dbeta, dbias partials: 3 x cols floats per warp) live in shared memory,
+// each warp read-modify-writing only its own slice with conflict-free 16-byte accesses; holding them in registers cost
+// 72 registers per thread and capped the kernel at 12 warps per SM, latency-bound at 40% of the HBM roofline.
+constexpr int LNB_WARPS = 4;
+__device__ __forceinline__ void acc8_add(float* p, const float (&v)[8]) {
+  float4 a = *reinterpret_cast<float4*>(p), b = *reinterpret_cast<float4*>(p + 4);
+  a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+  b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
+  *reinterpret_cast<float4*>(p) = a;
+  *reinterpret_cast<float4*>(p + 4) = b;
+}
 template <typename TIn, int NVEC>
-__global__ void __launch_bounds__(LNB_WARPS * 32, NVEC <= 3 ? 3 : 2)
+__global__ void __launch_bounds__(LNB_WARPS * 32, NVEC <= 3 ? 5 : 3)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const TIn* __restrict__ x,
                      const bf16* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, bf16* __restrict__ dx_res, bf16* __restrict__ dx_dense,
@@ -238,16 +248,14 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
   pdl_trigger();
   pdl_wait();
   const DropCfg drop = resolve_drop(drop_in);
-  __shared__ float red[LNB_WARPS][32 * 8 + 1];
+  extern __shared__ __align__(16) float lnb_acc[];  // [LNB_WARPS][3][cols]
   constexpr int cols = NVEC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_cols = 1.0f / (float)cols;
   const bool emit = dx_res != nullptr || dx_dense != nullptr || dbias != nullptr;
-  float acc_g[NVEC][8], acc_b[NVEC][8], acc_x[NVEC][8];
-#pragma unroll
-  for (int i = 0; i < NVEC; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = acc_x[i][j] = 0.f;
+  float* my = lnb_acc + warp * 3 * cols;
+  for (int k = lane * 4; k < 3 * cols; k += 128) *reinterpret_cast<float4*>(my + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
 
   for (long long row = (long long)blockIdx.x * LNB_WARPS + warp; row < rows; row += (long long)gridDim.x * LNB_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -258,7 +266,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = (i * 32 + lane) * 8;
-      float d[8], gm[8];
+      float d[8], gm[8], dh[8];
       ln_bwd_load(dy, dy2, x, res, row * cols + c, drop, xh[i], d, keep[i]);
       load8(gamma + c, gm);
 #pragma unroll
@@ -267,11 +275,12 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
         const float gg = d[j] * gm[j];
         s1 += gg;
         s2 = fmaf(gg, h, s2);
-        acc_g[i][j] = fmaf(d[j], h, acc_g[i][j]);
-        acc_b[i][j] += d[j];
+        dh[j] = d[j] * h;
         xh[i][j] = h;
         g[i][j] = gg;
       }
+      acc8_add(my + c, dh);
+      acc8_add(my + cols + c, d);
     }
     if (!emit) continue;  // parameter gradients only
     s1 = warp_sum(s1);
@@ -285,29 +294,22 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
       for (int j = 0; j < 8; ++j) {
         dz[j] = fmaf(xh[i][j], b, fmaf(g[i][j], rstd, a));
         dd[j] = (drop.mode == 1) ? (((keep[i] >> j) & 1u) ? dz[j] * drop.scale : 0.f) : dz[j];
-        acc_x[i][j] += dd[j];
       }
+      if (dbias != nullptr) acc8_add(my + 2 * cols + c, dd);
       if (dx_res != nullptr) store8(dx_res + row * cols + c, dz);
       if (dx_dense != nullptr && dx_dense != dx_res) store8(dx_dense + row * cols + c, dd);
     }
   }
-  // column sums: reduce the LNB_WARPS partials through shared memory, one vector slot at a time
+  // column sums: add the LNB_WARPS slices, one atomic per column per CTA
+  __syncthreads();
   for (int which = 0; which < 3; ++which) {
     float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
     if (dst == nullptr) continue;
+    for (int e = threadIdx.x; e < cols; e += LNB_WARPS * 32) {
+      float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        red[warp][lane * 8 + j] = which == 0 ? acc_g[i][j] : which == 1 ? acc_b[i][j] : acc_x[i][j];
-      __syncthreads();
-      for (int e = threadIdx.x; e < 256; e += LNB_WARPS * 32) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < LNB_WARPS; ++w) t += red[w][e];
-        atomicAdd(dst + i * 256 + e, t);
-      }
+      for (int w = 0; w < LNB_WARPS; ++w) t += lnb_acc[(w * 3 + which) * cols + e];
+      atomicAdd(dst + e, t);
     }
   }
 }
@@ -316,11 +318,12 @@ template <typename TIn>
 static void launch_ln_bwd(int grid, cudaStream_t st, const bf16* dy, const bf16* dy2, const TIn* x, const bf16* res,
                           const float* gamma, const float* mean, const float* rstd, bf16* dx_res, bf16* dx_dense,
                           float* dgamma, float* dbeta, float* dbias, int rows, int cols, DropCfg drop) {
+  const size_t smem = (size_t)LNB_WARPS * 3 * cols * sizeof(float);
   switch (cols >> 8) {
-    case 1: launch_kernel(layernorm_bwd_kernel<TIn, 1>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
-    case 2: launch_kernel(layernorm_bwd_kernel<TIn, 2>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
-    case 3: launch_kernel(layernorm_bwd_kernel<TIn, 3>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
-    default: launch_kernel(layernorm_bwd_kernel<TIn, 4>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 1: launch_kernel(layernorm_bwd_kernel<TIn, 1>, dim3(grid), dim3(LNB_WARPS * 32), smem, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 2: launch_kernel(layernorm_bwd_kernel<TIn, 2>, dim3(grid), dim3(LNB_WARPS * 32), smem, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    case 3: launch_kernel(layernorm_bwd_kernel<TIn, 3>, dim3(grid), dim3(LNB_WARPS * 32), smem, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
+    default: launch_kernel(layernorm_bwd_kernel<TIn, 4>, dim3(grid), dim3(LNB_WARPS * 32), smem, st, dy, dy2, x, res, gamma, mean, rstd, dx_res, dx_dense, dgamma, dbeta, dbias, rows, drop); break;
   }
 }
 
@@ -344,7 +347,7 @@ static DropCfg make_drop(int mode, float p, const unsigned long long* rng, unsig
 
 static int lnb_grid(int rows) {
   long long blocks = ((long long)rows + LNB_WARPS - 1) / LNB_WARPS;
-  const long long cap = 148LL * 3 * 4;
+  const long long cap = 148LL * 5;
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 static int ln_grid(int rows) {

@@ -176,12 +176,15 @@ def attention_fwd(q, k, v, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0):
     return o, lse
 
 
-def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0):
+def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0, dbias=None):
+    """dbias: optional (dbq, dbk, dbv) fp32 [H] tensors; the kernel adds the column sums of dq / dk / dv (the projection
+    bias gradients) to them, which saves the separate column-sum pass over the [T, 3H] gradient."""
+    dbq, dbk, dbv = dbias if dbias is not None else (None, None, None)
     call("univl_attention_bwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
          o.data_ptr(), o.stride(0), lse.data_ptr(), d_o.data_ptr(), d_o.stride(0), dq.data_ptr(), dq.stride(0),
          dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), ptr(mask.a), ptr(mask.b), mask.Wa, mask.Fb,
          mask.Nb, int(mask.all_pairs), n_seq, HEADS, Sq, Sk, int(mask.causal), 1.0 / math.sqrt(64.0), float(p), seed,
-         stream)
+         stream, ptr(dbq), ptr(dbk), ptr(dbv))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -249,8 +252,7 @@ def attn_block_bwd(dy, dy2, sv, need_dxkv=True):
         dqkv = _empty((T, 3 * H), BF16, dy)
         attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctx"], sv["lse"], dctx, dqkv[:, :H],
                       dqkv[:, H:2 * H], dqkv[:, 2 * H:], sv["n_seq"], sv["Sq"], sv["Sk"], sv["mask"], sv["pa"],
-                      sv["seed"], sv["sa"])
-        colsum(dqkv, dbqkv)
+                      sv["seed"], sv["sa"], dbias=(dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]))
         linear_wgrad(dqkv, sv["xq"], dwqkv)
         dxq = linear_dgrad(dqkv, sv["wqkv"], epi=EPI_ADD, aux_in=g)
         dxkv = None
@@ -259,11 +261,10 @@ def attn_block_bwd(dy, dy2, sv, need_dxkv=True):
         dq = _empty((T, H), BF16, dy)
         dkv = _empty((Tk, 2 * H), BF16, dy)
         attention_bwd(q, kv[:, :H], kv[:, H:], sv["ctx"], sv["lse"], dctx, dq, dkv[:, :H], dkv[:, H:], sv["n_seq"],
-                      sv["Sq"], sv["Sk"], sv["mask"], sv["pa"], sv["seed"], sv["sa"])
+                      sv["Sq"], sv["Sk"], sv["mask"], sv["pa"], sv["seed"], sv["sa"],
+                      dbias=(dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]))
         linear_wgrad(dq, sv["xq"], dwqkv[:H])
         linear_wgrad(dkv, sv["xkv"], dwqkv[H:])
-        colsum(dq, dbqkv[:H])
-        colsum(dkv, dbqkv[H:])
         dxq = linear_dgrad(dq, sv["wqkv"][:H], epi=EPI_ADD, aux_in=g)
         dxkv = linear_dgrad(dkv, sv["wqkv"][H:]) if need_dxkv else None
     rets = {"q": r_w[0], "k": r_w[1], "v": r_w[2], "bq": r_b[0], "bk": r_b[1], "bv": r_b[2], "o": r_o, "bo": r_bo,
