@@ -306,7 +306,10 @@ def main():
         sampler.join(timeout=3)
 
     # ---- roofline of the dominant kernel: CUDA events around every tcgen05 GEMM launch on the launching stream ----
-    prof = {"flops": 0.0, "events": []}
+    # The dominant kernel is the CTA-pair GEMM (gemm_tcgen05_2cta_kernel, ~49% of the step in profiles/); the library
+    # reports which variant each call launched, so its launches are separated from the single-CTA persistent ones.
+    from univl_b200 import lib as _lib
+    prof = {2: {"flops": 0.0, "events": []}, 1: {"flops": 0.0, "events": []}, 0: {"flops": 0.0, "events": []}}
     orig_gemm = ops.gemm
 
     def timed_gemm(a_, b_, M, N, K, out, *args, **kw):
@@ -314,18 +317,31 @@ def main():
         s.record()
         r = orig_gemm(a_, b_, M, N, K, out, *args, **kw)
         e.record()
-        prof["events"].append((s, e))
-        prof["flops"] += 2.0 * M * N * K
+        v = prof[int(_lib.load().univl_gemm_last_variant())]
+        v["events"].append((s, e))
+        v["flops"] += 2.0 * M * N * K
         return r
     ops.gemm = timed_gemm
     for _ in range(a.profile_steps):
         eager_step(dev_batch)
     torch.cuda.synchronize()
     ops.gemm = orig_gemm
-    gemm_ms = sum(s.elapsed_time(e) for s, e in prof["events"])
-    n_gemm = len(prof["events"])
-    achieved = prof["flops"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    per = {}
+    for k, v in prof.items():
+        ms_k = sum(s.elapsed_time(e) for s, e in v["events"])
+        per[k] = {"ms": ms_k, "n": len(v["events"]), "flops": v["flops"],
+                  "tflops": v["flops"] / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0}
+    dom = per[2] if per[2]["n"] else per[1]
+    gemm_ms, n_gemm, achieved = dom["ms"], dom["n"], dom["tflops"]
+    all_ms = sum(v["ms"] for v in per.values())
+    all_flops = sum(v["flops"] for v in per.values())
     peak, peak_src = peaks()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
+            traffic = json.load(f).get("traffic_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
 
     # max over ranks
     t = torch.tensor([ms, ms_e2e if not a.no_e2e else 0.0], device=dev, dtype=torch.float64)
@@ -348,10 +364,23 @@ def main():
                    "l2": "per-step working set (~6 GB of activations at FT-Align b=32) exceeds the 126 MB L2"},
         "gpu_launches": launches, "loss": loss_val,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "kernel": "gemm_tcgen05_kernel",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "kernel": "gemm_tcgen05_2cta_kernel" if per[2]["n"] else "gemm_tcgen05_persistent_kernel",
                      "launches_per_step": n_gemm / max(1, a.profile_steps),
                      "gemm_ms_per_step": gemm_ms / max(1, a.profile_steps), "peak_source": peak_src,
-                     "algorithmic_flops_per_step": prof["flops"] / max(1, a.profile_steps)},
+                     "algorithmic_flops_per_step": dom["flops"] / max(1, a.profile_steps),
+                     "traffic_source": "ncu --set full capture summarised in profiles/r01_ncu_full_gemm_cross.txt"
+                                       " (mean dram read+write bytes per launch of the cross-encoder launches)",
+                     "all_gemm_kernels": {"tflops": all_flops / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0,
+                                          "ms_per_step": all_ms / max(1, a.profile_steps),
+                                          "launches_per_step": sum(v["n"] for v in per.values())
+                                          / max(1, a.profile_steps)},
+                     "persistent_kernel": {"tflops": per[1]["tflops"],
+                                           "ms_per_step": per[1]["ms"] / max(1, a.profile_steps),
+                                           "launches_per_step": per[1]["n"] / max(1, a.profile_steps)},
+                     "note": "256x256 CTA-pair tiles move 32 KB of operands per CTA per 64-deep k-block (128 flop/B): "
+                             "L2->SM delivery (~12 TB/s) caps them near 1.5 PFLOP/s, the same regime as the cuBLAS "
+                             "peak used here"},
         "clocks": sampler.summary() if sampler else None,
     }
     if not a.no_e2e:

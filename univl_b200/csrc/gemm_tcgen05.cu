@@ -434,6 +434,11 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 
 using namespace univl;
 
+static int g_last_variant = -1;
+// which kernel the most recent univl_gemm_bf16 call on this process launched: 2 = CTA-pair (gemm_tcgen05_2cta_kernel),
+// 1 = single-CTA persistent, 0 = bring-up kernel, -1 = none yet.  Measurement aid for bench.py's per-kernel roofline.
+extern "C" int univl_gemm_last_variant(void) { return g_last_variant; }
+
 extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                                int b_mn_major, int M, int N, int Kc, void* out, long long ldo, int epilogue,
                                const float* bias, const void* aux_in, long long ld_aux_in, void* aux_out,
@@ -538,11 +543,13 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
       tx = ta;
     }
     p.tma_epilogue = tma_ok ? 1 : 0;
+    g_last_variant = pair ? 2 : 1;
     if (pair) return dispatch_major_2<256, 5>(amn, bmn, ta, tb, to, tx, p, splits, stream);
     if (bn == 256) return dispatch_major_p<256, 3>(amn, bmn, ta, tb, to, tx, p, splits, stream);
     if (bn == 128) return dispatch_major_p<128, 5>(amn, bmn, ta, tb, to, tx, p, splits, stream);
     return dispatch_major_p<64, 6>(amn, bmn, ta, tb, to, tx, p, splits, stream);
   }
+  g_last_variant = 0;
   if (bn == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, p, splits, stream);
   if (bn == 128) return dispatch_major<128, 3>(amn, bmn, ta, tb, p, splits, stream);
   return dispatch_major<64, 4>(amn, bmn, ta, tb, p, splits, stream);
