@@ -138,7 +138,8 @@ def _attn_ref(q, k, v, add_mask):
 
 
 @pytest.mark.parametrize("n_seq,Sq,Sk,causal", [(3, 48, 48, False), (2, 96, 96, False), (2, 20, 52, False),
-                                                 (2, 128, 128, True), (1, 224, 224, False), (2, 33, 33, True)])
+                                                 (2, 128, 128, True), (1, 224, 224, False), (2, 33, 33, True),
+                                                 (3, 1, 96, False)])  # Sq = 1: first-token-only last cross layer
 def test_attention_fwd_bwd(n_seq, Sq, Sk, causal):
     H, h = 768, 12
     g = torch.Generator(device=DEV).manual_seed(Sq + Sk)

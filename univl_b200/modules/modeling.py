@@ -181,8 +181,9 @@ class UniVL(UniVLPreTrainedModel):
         The reference walks text rows in chunks of 5 and `repeat`s both sides; here all B_t x B_v sequences go
         through the layer kernels in one batch and the embedding kernel reads the un-repeated sources."""
         bt, bv = attention_mask.shape[0], video_mask.shape[0]
-        hidden, n_seq, S = self._cross_pairs(seq2d, vis2d, attention_mask, video_mask, True)
-        u = self.cross.pooler.pre_activation(hidden, n_seq, S)
+        # only token 0 of the last cross layer feeds the pooler: the last layer computes just those rows
+        first, n_seq = self.cross.encode_pairs_first_token(seq2d, vis2d, attention_mask, video_mask, True)
+        u = self.cross.pooler.pre_activation(first, n_seq, 1)
         logits = ops.PoolerSimFn.apply(u, self.similarity_dense.weight, self.similarity_dense.bias)
         return logits.view(bt, bv)
 

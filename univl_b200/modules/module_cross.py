@@ -73,6 +73,17 @@ class CrossModel(PreTrainedModel):
         mask = ops.MaskSpec(text_mask, video_mask, all_pairs=all_pairs)
         return self.encoder.run(x, n_seq, W + F, mask, keep_all=keep_all), n_seq, W + F
 
+    def encode_pairs_first_token(self, text2d, video2d, text_mask, video_mask, all_pairs):
+        """as encode_pairs, but only token 0 of every sequence of the LAST layer is produced: [n_seq, H].  The pooled
+        similarity head (reference modeling.py:371-373) reads nothing else, so the last layer skips the query side of
+        the other W+F-1 tokens."""
+        Nt, W = text_mask.shape
+        Nv, F = video_mask.shape
+        n_seq = Nt * Nv if all_pairs else Nt
+        x = self.embeddings.run(text2d, video2d, Nt, W, Nv, F, all_pairs)
+        mask = ops.MaskSpec(text_mask, video_mask, all_pairs=all_pairs)
+        return self.encoder.run_first_token(x, n_seq, W + F, mask), n_seq
+
     def forward(self, concat_input, concat_type=None, attention_mask=None, output_all_encoded_layers=True):
         """API-parity entry: `concat_type` must be the reference's layout (0s for the text part then 1s)."""
         N, S, _ = concat_input.shape

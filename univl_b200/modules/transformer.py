@@ -102,6 +102,11 @@ class EncoderLayer(nn.Module):
                                         self.attention.self.dropout.p, self.training, *params)
 
 
+def _layer_params(layer):
+    return attention_param_list(layer.attention.self, layer.attention.output) + \
+        ffn_param_list(layer.intermediate, layer.output)
+
+
 class EncoderStack(nn.Module):
     """`encoder.layer.N` (reference modules/module_bert.py:267-281)."""
 
@@ -116,6 +121,15 @@ class EncoderStack(nn.Module):
             if keep_all:
                 outs.append(x2d)
         return outs if keep_all else x2d
+
+    def run_first_token(self, x2d, n_seq, S, mask):
+        """-> [n_seq, H]: token 0 of the last layer's output, for consumers that read nothing else (pooler).  All layers
+        but the last run in full; the last one computes only what token 0 needs (ops.EncoderLayerClsFn)."""
+        for layer in self.layer[:-1]:
+            x2d = layer.run(x2d, n_seq, S, mask)
+        last = self.layer[-1]
+        return ops.EncoderLayerClsFn.apply(x2d, n_seq, S, mask, last.attention.output.dropout.p,
+                                           last.attention.self.dropout.p, last.training, *_layer_params(last))
 
 
 class Pooler(nn.Module):

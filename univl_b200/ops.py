@@ -335,6 +335,40 @@ class EncoderLayerFn(torch.autograd.Function):
             tuple(gf[k] for k in FFN_KEYS)
 
 
+class EncoderLayerClsFn(torch.autograd.Function):
+    """The LAST layer of an encoder stack whose only consumer reads token 0 of every sequence (the cross encoder under
+    `_cross_similarity`: pooler -> similarity_dense, reference modules/modeling.py:371-373 with module_cross.py:281-287).
+    Token 0 of the layer output depends on the other tokens only through their keys and values, and the dense / FFN /
+    LayerNorm stages are row-wise, so the query side (Q projection, softmax row, output projection, both LayerNorms, the
+    FFN) runs on the n_seq first-token rows instead of all n_seq*S rows; K/V projections stay dense.  Same numbers for
+    the rows that are used, same gradients (the unused rows receive exactly zero gradient in the dense form too).
+    args as EncoderLayerFn; returns [n_seq, H]."""
+
+    @staticmethod
+    def forward(ctx, x, n_seq, S, mask, p_hidden, p_attn, training, *params):
+        wa = dict(zip(ATT_KEYS, params[:10]))
+        wf = dict(zip(FFN_KEYS, params[10:16]))
+        drop = _Drop(p_hidden, p_attn, training)
+        H = x.shape[1]
+        xq = x.view(n_seq, S, H)[:, 0].contiguous()
+        y1, sva = attn_block_fwd(xq, x, n_seq, 1, S, mask, wa, drop)
+        y2, svf = ffn_block_fwd(y1, wf, drop)
+        ctx.sva, ctx.svf = sva, svf
+        ctx.shape = (n_seq, S, H)
+        return y2
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        n_seq, S, H = ctx.shape
+        g2, dy1, gf = ffn_block_bwd(dy, ctx.svf)
+        dxq, dxkv, ga = attn_block_bwd(dy1, g2, ctx.sva)
+        dxkv.view(n_seq, S, H)[:, 0].add_(dxq)  # the first-token rows are both a query source and a key/value source
+        ctx.sva = ctx.svf = None
+        return (dxkv, None, None, None, None, None, None) + tuple(ga[k] for k in ATT_KEYS) + \
+            tuple(gf[k] for k in FFN_KEYS)
+
+
 class DecoderLayerFn(torch.autograd.Function):
     """One DecoderLayer (reference modules/module_decoder.py:279-292): causal self-attention block, encoder-attention
     block, FFN block.  args: x[Td,H], enc[Te,H], then 10 + 10 + 6 params."""
