@@ -1,0 +1,1 @@
+"""CPU oracle (test infrastructure only): restatement of the reference algorithm, pinned to reference goldens."""
