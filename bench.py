@@ -383,10 +383,12 @@ def main():
     all_ms = sum(v["ms"] for v in per.values())
     all_flops = sum(v["flops"] for v in per.values())
     peak, peak_src = peaks()
-    traffic = None
+    traffic, pipe_util = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")) as f:
-            traffic = json.load(f).get("traffic_bytes_per_launch")
+            captured = json.load(f)
+        traffic = captured.get("traffic_bytes_per_launch")
+        pipe_util = captured.get("tensor_pipe_util_pct")  # BASELINE's second metric: ncu figures, not timed here
     except (OSError, ValueError):
         pass
 
@@ -429,6 +431,7 @@ def main():
                              "L2->SM delivery (~12 TB/s) caps them near 1.5 PFLOP/s, the same regime as the cuBLAS "
                              "peak used here"},
         "clocks": sampler.summary() if sampler else None,
+        "tensor_pipe_util_pct": pipe_util,
     }
     if not a.no_e2e:
         line["e2e"] = {"value": samples / (ms_e2e_max * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
