@@ -2,8 +2,8 @@
 //
 // Same math and operand conventions as gemm_tcgen05_kernel, restructured so the tensor pipe never waits for the
 // epilogue:
-//   * grid = min(#work items, #SMs); each CTA (or CTA pair) walks work items (m-tile fastest, then n-tile, then
-//     k-split) round-robin
+//   * grid = min(#work items, #SMs); each CTA (or CTA pair) walks work items round-robin in the order decode_work()
+//     defines (n-tile fastest without split-K so activation tiles are re-read from L2; split-major with split-K)
 //   * TWO accumulator buffers in TMEM (2 x BLOCK_N fp32 columns): the MMA warp fills buffer (t+1)&1 while the eight
 //     epilogue warps drain buffer t&1 (tmem_full / tmem_empty mbarriers per buffer)
 //   * the TMA producer's smem ring runs continuously across tiles (no pipeline drain between tiles)
