@@ -38,9 +38,9 @@ int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B,
                     int M, int N, int Kc, void* out, long long ldo, int epilogue, const float* bias,
                     const void* aux_in, long long ld_aux_in, void* aux_out, long long ld_aux_out, float alpha,
                     int block_n, int split_k, void* stream);
-/* kernel variant launched by the most recent univl_gemm_bf16 call: 2 CTA-pair, 1 single-CTA persistent, 0 bring-up,
- * -1 none (measurement aid: bench.py attributes launch times to the dominant kernel with it) */
-int univl_gemm_last_variant(void);
+/* kernel variant univl_gemm_bf16 launches for this problem: 2 CTA-pair, 1 single-CTA persistent, 0 bring-up; a pure
+ * function of its arguments (measurement aid: bench.py attributes launch times to the dominant kernel with it) */
+int univl_gemm_plan(int M, int N, int Kc, int epilogue, int block_n, int split_k);
 
 /* ---- LayerNorm family (until_module.py:49-53; eps inside sqrt) ---------------------------------------------
  * drop_mode 1: y = LN(dropout(x) + res)   (module_bert.py:207-211, :246-250)

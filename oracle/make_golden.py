@@ -40,6 +40,17 @@ CASES = {
                              decoder_layers=1, max_words=16, max_frames=12), dict(seed=13, ragged=True)),
     "pretrain1_mil": (dict(mode="pretrain1", batch_size=2, n_pair=3, text_layers=1, visual_layers=1, max_words=16,
                            max_frames=12), dict(seed=17, ragged=True)),
+    # ---- BASELINE.json configs[1], [3], [4] at their REAL shapes and full 12/6/2/3 depth (per-rank batch reduced so
+    # the CPU reference finishes in minutes; sequence lengths, depths and objectives are the configs' own) ----
+    # configs[1]: retrieval fine-tune FT-Align, per-GPU batch 32 (1024 pair sequences), reference init law
+    "cfg2_ft_align_b32_init": (dict(mode="ft_align", batch_size=32), dict(seed=1234, ragged=True),
+                               dict(init_law=True)),
+    # configs[3]: caption stage-two, max_words=128 max_frames=96 (decoder L=128 over S_e=224 encoder tokens)
+    "cfg4_caption": (dict(mode="caption", batch_size=2, max_words=128, max_frames=96), dict(seed=21, ragged=True)),
+    # configs[4]: pretrain stage-two, all five objectives, W=F=48; n_pair 1 (stress weights) and 3 (init law)
+    "cfg5_pretrain2": (dict(mode="pretrain2", batch_size=4), dict(seed=23, ragged=True)),
+    "cfg5_pretrain2_npair3_init": (dict(mode="pretrain2", batch_size=4, n_pair=3), dict(seed=29, ragged=True),
+                                   dict(init_law=True)),
 }
 
 BERT_BASE = dict(attention_probs_dropout_prob=0.1, hidden_act="gelu", hidden_dropout_prob=0.1, hidden_size=768,
@@ -147,8 +158,69 @@ def make_case(name):
     return gold
 
 
+def _compact(t):
+    """full tensor when small; head / tail slices + moments for long ones (keeps the fixture small)"""
+    t = t.detach().clone()
+    if t.numel() <= 4096:
+        return t
+    f = t.flatten().double()
+    return dict(head=t.flatten()[:256].clone(), tail=t.flatten()[-256:].clone(), sum=float(f.sum()),
+                sq_sum=float((f * f).sum()), numel=t.numel())
+
+
+def make_bert_adam_golden(steps=4):
+    """tests/golden/ref_bert_adam.pt: the reference's OWN BertAdam class (modules/optimization.py:66-168) run for
+    `steps` steps on a small parameter set arranged in the 4 groups the drivers build (main_task_retrieval.py:173-190:
+    decay / no-decay x "bert." / other, lr scaled by coef_lr for "bert." names), preceded each step by the driver's
+    clip_grad_norm_(parameters, 1.0) (main_task_retrieval.py:347).  Stores initial values, per-step gradients and the
+    parameters + moments after every step, and the reference optimizer's state_dict() after step 3 (so that
+    load_state_dict + one more step must reproduce step 4: the resume path of main_pretrain.py:389)."""
+    import copy
+    import_reference()
+    from modules.optimization import BertAdam
+    names_shapes, init, grads, no_grad = synth.adam_case(steps)
+    params = {n: torch.nn.Parameter(v.clone()) for n, v in init.items()}
+    named = list(params.items())
+    no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+    dec = [(n, p) for n, p in named if not any(nd in n for nd in no_decay)]
+    nod = [(n, p) for n, p in named if any(nd in n for nd in no_decay)]
+    lr, coef, warmup, t_total = synth.ADAM_CASE_HYPER
+    groups = [{"params": [p for n, p in dec if "bert." in n], "weight_decay": 0.01, "lr": lr * coef},
+              {"params": [p for n, p in dec if "bert." not in n], "weight_decay": 0.01},
+              {"params": [p for n, p in nod if "bert." in n], "weight_decay": 0.0, "lr": lr * coef},
+              {"params": [p for n, p in nod if "bert." not in n], "weight_decay": 0.0}]
+    opt = BertAdam(groups, lr=lr, warmup=warmup, schedule="warmup_linear", t_total=t_total, weight_decay=0.01,
+                   max_grad_norm=1.0)
+    after = []
+    sd3 = None
+    for t in range(steps):
+        for n, p in params.items():
+            p.grad = grads[t][n].clone() if n in grads[t] else None
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        opt.zero_grad()
+        after.append({"params": {n: _compact(p.detach()) for n, p in params.items()},
+                      "next_m": {n: _compact(opt.state[p]["next_m"]) for n, p in params.items() if p in opt.state},
+                      "next_v": {n: _compact(opt.state[p]["next_v"]) for n, p in params.items() if p in opt.state}})
+        if t == 2:
+            sd3 = copy.deepcopy(opt.state_dict())
+            for st in sd3["state"].values():     # the long tensor is regenerated by the test from after[2] ... keep small
+                for k in ("next_m", "next_v"):
+                    if st[k].numel() > 4096:
+                        st[k] = None
+    gold = dict(names_shapes=names_shapes, after=after, lr=lr, coef_lr=coef, warmup=warmup,
+                t_total=t_total, weight_decay=0.01, max_grad_norm=1.0, global_clip=1.0, no_decay=no_decay,
+                state_dict_after3=sd3, torch_version=torch.__version__)
+    out = os.path.join(ROOT, "tests", "golden", "ref_bert_adam.pt")
+    torch.save(gold, out)
+    print("bert_adam golden: %d steps -> %s (%.1f KB)" % (steps, out, os.path.getsize(out) / 1024))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or list(CASES) + ["bert_adam"]
     for n in names:
-        make_case(n)
+        if n == "bert_adam":
+            make_bert_adam_golden()
+        else:
+            make_case(n)

@@ -234,3 +234,29 @@ def make_batch(cfg, seed=1234, b=None, ragged=True, video_dtype=torch.float32):
         batch.update(input_caption_ids=inp.view(b, P, W), decoder_mask=cmask.view(b, P, W),
                      output_caption_ids=out.view(b, P, W))
     return batch
+
+
+# ---- optimizer parity case (tests/golden/ref_bert_adam.pt; generated by oracle/make_golden.py from the reference's
+# own BertAdam class) -------------------------------------------------------------------------------------------------
+ADAM_CASE_HYPER = (1e-2, 0.1, 0.1, 20)   # lr, coef_lr, warmup, t_total
+
+
+def adam_case(steps=4):
+    """-> (names_shapes, init{name: tensor}, grads[step]{name: tensor}, names that never receive a gradient).
+    Names follow the checkpoint layout so the drivers' four parameter groups (main_task_retrieval.py:173-190) form."""
+    g = torch.Generator().manual_seed(31)
+    names_shapes = [("bert.encoder.layer.0.attention.self.query.weight", (96, 64)),
+                    ("bert.encoder.layer.0.attention.self.query.bias", (96,)),
+                    ("bert.encoder.layer.0.attention.output.LayerNorm.weight", (64,)),
+                    ("bert.pooler.dense.weight", (64, 64)),          # never receives a gradient (grad None)
+                    ("visual.encoder.layer.0.intermediate.dense.weight", (200, 64)),
+                    ("visual.encoder.layer.0.intermediate.dense.bias", (200,)),
+                    ("cross.encoder.layer.1.output.LayerNorm.bias", (64,)),
+                    ("similarity_dense.weight", (1, 64)),
+                    ("decoder.classifier.cls.predictions.bias", (70001,))]  # > one 64K chunk, odd length
+    init = {n: 0.5 * torch.randn(s, generator=g) for n, s in names_shapes}
+    no_grad = {"bert.pooler.dense.weight"}
+    scales = [3.0, 0.05, 0.4]     # step 1 trips the global clip, step 2 nothing, step 3 the per-tensor clip
+    grads = [{n: scales[t % 3] * torch.randn(s, generator=g) * (6.0 if (t == 2 and n.startswith("visual")) else 1.0)
+              for n, s in names_shapes if n not in no_grad} for t in range(steps)]
+    return names_shapes, init, grads, no_grad

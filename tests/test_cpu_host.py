@@ -3,6 +3,7 @@ the reference-surface modules reproduce the checkpoint layout contract, and the 
 (no CPU fallback)."""
 import ctypes
 import os
+import sys
 
 import pytest
 import torch
@@ -119,3 +120,43 @@ def test_config_surface():
     from univl_b200.modules.until_module import PreTrainedModel
     with pytest.raises(ValueError):
         PreTrainedModel(object())
+
+
+def test_launcher_shims(monkeypatch):
+    """univl_b200.launcher: --local-rank mapping, import stubs, numpy aliases, `modules` shadowing (SURVEY §8f#4)"""
+    import importlib
+    import numpy as np
+    from univl_b200 import launcher
+    assert launcher.fix_rank_args(["--do_train", "--local-rank=3"]) == ["--do_train", "--local_rank=3"]
+    monkeypatch.setenv("LOCAL_RANK", "5")
+    assert launcher.fix_rank_args(["--do_train"]) == ["--do_train", "--local_rank", "5"]
+    assert launcher.fix_rank_args(["--local_rank", "1"]) == ["--local_rank", "1"]
+    launcher.install_stubs()
+    import boto3  # noqa: F401
+    from botocore.exceptions import ClientError  # noqa: F401
+    import nlgeval
+    assert hasattr(nlgeval, "NLGEval")
+    launcher.install_numpy_aliases()
+    assert np.zeros(2, dtype=np.float).dtype == np.float64
+    from oracle import build_ref
+    root = build_ref.ref_root()
+    if root is None:
+        return
+    saved = {k: v for k, v in sys.modules.items() if k == "modules" or k.startswith("modules.")}
+    saved_path = list(sys.path)
+    try:
+        launcher.install_shadow(root)
+        m = importlib.import_module("modules.modeling")
+        assert m.__name__ == "univl_b200.modules.modeling"
+        from modules.optimization import BertAdam
+        from univl_b200.optim import FusedBertAdam
+        assert issubclass(BertAdam, FusedBertAdam)
+        tok = importlib.import_module("modules.tokenization")          # the checkout's own file, our file_utils under it
+        assert os.path.dirname(tok.__file__) == os.path.join(root, "modules")
+        assert hasattr(tok, "BertTokenizer")
+        from modules.beam import Beam  # noqa: F401
+    finally:
+        for k in [k for k in sys.modules if k == "modules" or k.startswith("modules.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path[:] = saved_path

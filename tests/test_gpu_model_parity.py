@@ -9,7 +9,11 @@ Stated tolerances (bf16 activations, fp32 accumulation / statistics / losses; th
          cross-entropy losses over the vocabulary / frames (caption, pretrain-II):            |d| <= 2e-3 * |loss|
          MIL-NCE on UN-normalised dot products (use_mil): |d| <= 2^-8 * max|sim| — the logits are only resolved to
          bf16 precision relative to their magnitude (~25 here)
-  hidden states   max abs err <= 6e-2 on values of magnitude ~4
+  hidden states   relative Frobenius error <= (layers + 1) * 2^-9: one worst-case bf16 round-to-nearest error (2^-9
+                  relative) per layer of the stack, accumulated linearly (+1 for the embedding).  The expected value under
+                  independent roundings is sqrt(7 roundings x layers) * 2^-9 / sqrt(3) = 1.0e-2 for the 12-layer text
+                  stack, so the bound leaves ~2x; the achieved margins are written to gpurun_out/parity_margins.json and
+                  listed in DESIGN.md.  Worst single element: 0.1 absolute on values of magnitude 2-4 (~6 bf16 ulps).
   gradients       per tensor ||g - g_oracle|| <= 0.10 * max(||g_oracle||, 0.05 * largest gradient norm) and, for tensors
                   above that floor, norm within 6 %.  The floor exists because some gradients are mathematically (key
                   biases: softmax shift invariance) or numerically (q/k weights of deep layers once attention has
@@ -27,8 +31,27 @@ from tests.oracle_util import load_golden, run_oracle
 
 pytestmark = pytest.mark.gpu
 
+import json
+import os
+
 CASES = ["ft_joint_npair2", "pretrain1_mil", "caption_small", "pretrain2_small", "cfg1_ft_joint", "cfg1_ft_align",
-         "cfg1_ft_joint_init", "cfg1_ft_align_init"]
+         "cfg1_ft_joint_init", "cfg1_ft_align_init",
+         # BASELINE.json configs[3], [4], [1] at their real sequence lengths and full 12/6/2/3 depth
+         "cfg4_caption", "cfg5_pretrain2", "cfg5_pretrain2_npair3_init", "cfg2_ft_align_b32_init"]
+GOLDEN_ONLY = {"cfg2_ft_align_b32_init"}   # 1024 pair sequences: checked against the reference's stored outputs only
+
+_MARGINS = {}
+
+
+def _record(name, **kw):
+    _MARGINS.setdefault(name, {}).update(kw)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_margins.json"), "w") as fh:
+            json.dump(_MARGINS, fh, indent=1, sort_keys=True)
+    except OSError:
+        pass
 
 
 def loss_tolerance(cfg, gold):
@@ -53,36 +76,68 @@ def test_loss_hidden_and_grads_match_reference(name):
     torch.cuda.synchronize()
     got = float(loss.detach())
     tol = loss_tolerance(cfg, gold)
+    _record(name, loss=got, ref_loss=gold["loss"], loss_err=abs(got - gold["loss"]), loss_tol=tol)
     assert abs(got - gold["loss"]) <= tol, "loss %r vs reference %r (tol %g)" % (got, gold["loss"], tol)
+    grads = grads_by_name(model)
+    assert set(grads) == set(gold["grad_norms"]), sorted(set(grads) ^ set(gold["grad_norms"]))[:8]
+    biggest = max(gold["grad_norms"].values())
+    floor = 0.05 * biggest
 
-    o_loss, parts, o_grads = run_oracle(cfg, batch, sd=sd, backward=True)
-    assert abs(got - float(o_loss)) <= tol
     model.eval()
     with torch.no_grad():
         b = to_device(batch)
         seq, vis = model.get_sequence_visual_output(b["input_ids"], b["token_type_ids"], b["attention_mask"],
                                                     b["video"], b["video_mask"])
+        if gold["sim_matrices"] and cfg.mode in ("ft_joint", "ft_align"):
+            sim = model.get_similarity_logits(seq, vis, b["attention_mask"], b["video_mask"]).float().cpu()
+            ref_sim = gold["sim_matrices"][-1]
+            sim_err = float((sim - ref_sim).abs().max())
+            _record(name, sim_max_err=sim_err, sim_scale=float(ref_sim.abs().max()))
+            assert sim_err <= 2.0 ** -7 * max(1.0, float(ref_sim.abs().max())), sim_err
     seq, vis = seq.float().cpu(), vis.float().cpu()
-    # hidden states after a 12-layer bf16 stack against the fp32 reference: values are O(1) (LayerNorm outputs), the
-    # bf16 storage rounding alone is 2^-9 relative per layer.  Bound the bulk (relative Frobenius error) tightly and the
-    # worst single element (a max over 10^4-10^5 elements, i.e. the noise tail) at ~6 bf16 ulps of |x| = 2..4.
-    for ours, ref in ((seq, parts["sequence_output"].detach()), (vis, parts["visual_output"].detach())):
-        assert float((ours - ref).norm() / ref.norm()) <= 2e-2  # 1.2e-2 measured on the 2x-init-std stress weights
-        assert float((ours - ref).abs().max()) <= 1e-1
     assert (seq[:, :6, :16] - gold["seq_slice"]).abs().max() <= 1e-1
+    assert (vis[:, :6, :16] - gold["vis_slice"]).abs().max() <= 1e-1
+    # Frobenius norm of the reference's hidden states from the stored sum of squares
+    for tag, ours, summ in (("seq", seq, gold["seq_summary"]), ("vis", vis, gold["vis_summary"])):
+        rel = abs(float(ours.double().norm()) - summ["sq_sum"] ** 0.5) / summ["sq_sum"] ** 0.5
+        _record(name, **{tag + "_norm_rel_err": rel})
+        assert rel <= 2.0 ** -9 * 4, (tag, rel)
 
-    grads = grads_by_name(model)
-    assert set(grads) == set(gold["grad_norms"]), sorted(set(grads) ^ set(gold["grad_norms"]))[:8]
-    biggest = max(gold["grad_norms"].values())
-    floor = 0.05 * biggest
+    if name in GOLDEN_ONLY:
+        worst = 0.0
+        for k, ref_norm in gold["grad_norms"].items():
+            if ref_norm < floor:
+                continue
+            ratio = float(grads[k].double().norm()) / ref_norm
+            worst = max(worst, abs(ratio - 1.0))
+        _record(name, grad_norm_worst_rel=worst)
+        assert worst <= 0.06, worst
+        return
+
+    o_loss, parts, o_grads = run_oracle(cfg, batch, sd=sd, backward=True)
+    assert abs(got - float(o_loss)) <= tol
+    # hidden states after an L-layer bf16 stack against the fp32 reference algorithm: derived bound (L + 1) * 2^-9 on the
+    # relative Frobenius error (see the module docstring); worst single element ~6 bf16 ulps of |x| = 2..4.
+    for tag, ours, ref, layers in (("seq", seq, parts["sequence_output"].detach(), cfg.text_num_hidden_layers),
+                                   ("vis", vis, parts["visual_output"].detach(), cfg.visual_num_hidden_layers)):
+        rel = float((ours - ref).norm() / ref.norm())
+        bound = (layers + 1) * 2.0 ** -9
+        _record(name, **{tag + "_rel_fro": rel, tag + "_bound": bound, tag + "_max_abs": float((ours - ref).abs().max())})
+        assert rel <= bound, (tag, rel, bound)
+        assert float((ours - ref).abs().max()) <= 1e-1
+
     bad = []
     emu = None
+    worst_err, worst_ratio, n_emu = 0.0, 0.0, 0
     for k, ref_norm in gold["grad_norms"].items():
         g, r = grads[k].double(), o_grads[k].double()
         abs_err = float((g - r).norm())
         err = abs_err / max(float(r.norm()), floor)
         ratio = float(g.norm()) / max(ref_norm, 1e-30)
         if err <= 0.10 and (ref_norm < floor or 0.94 <= ratio <= 1.06):
+            worst_err = max(worst_err, err)
+            if ref_norm >= floor:
+                worst_ratio = max(worst_ratio, abs(ratio - 1.0))
             continue
         # ill-conditioned gradient (e.g. the all-pairs hinge loss at random init: d loss / d sim sums to zero while
         # every pair back-propagates nearly the same vector).  Budget: what rounding the reference algorithm's own
@@ -90,7 +145,10 @@ def test_loss_hidden_and_grads_match_reference(name):
         if emu is None:
             _, _, emu = run_oracle(cfg, batch, sd=sd, backward=True, bf16_emulation=True)
         emu_err = float((emu[k].double() - r).norm())
+        n_emu += 1
         if abs_err > 2.5 * emu_err:
             bad.append((k, round(err, 4), round(ratio, 4), "bf16-emulated oracle error %.3e vs ours %.3e" % (
                 emu_err, abs_err)))
+    _record(name, grad_worst_rel_err=worst_err, grad_worst_norm_dev=worst_ratio, grads_judged_by_bf16_emulation=n_emu,
+            grads_total=len(gold["grad_norms"]))
     assert not bad, "gradient mismatches (name, relative error, norm ratio): %s" % bad[:12]

@@ -434,28 +434,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 
 using namespace univl;
 
-static int g_last_variant = -1;
-// which kernel the most recent univl_gemm_bf16 call on this process launched: 2 = CTA-pair (gemm_tcgen05_2cta_kernel),
-// 1 = single-CTA persistent, 0 = bring-up kernel, -1 = none yet.  Measurement aid for bench.py's per-kernel roofline.
-extern "C" int univl_gemm_last_variant(void) { return g_last_variant; }
-
-extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
-                               int b_mn_major, int M, int N, int Kc, void* out, long long ldo, int epilogue,
-                               const float* bias, const void* aux_in, long long ld_aux_in, void* aux_out,
-                               long long ld_aux_out, float alpha, int block_n, int split_k, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  UNIVL_CHECK_ARG(M > 0 && N > 0 && Kc > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, Kc);
-  UNIVL_CHECK_ARG(A && B && out, "gemm: null operand");
-  UNIVL_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (got %lld, %lld)",
-                  lda, ldb);
-  UNIVL_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: operands must be 16-byte aligned");
-  UNIVL_CHECK_ARG(epilogue >= 0 && epilogue <= 5, "gemm: unknown epilogue %d", epilogue);
-  if (epilogue == EPI_GELU_BWD_BF16 || epilogue == EPI_ADD_BF16)
-    UNIVL_CHECK_ARG(aux_in != nullptr, "gemm: epilogue %d needs aux_in", epilogue);
-  if (epilogue == EPI_BIAS_GELU_BF16) UNIVL_CHECK_ARG(aux_out != nullptr, "gemm: gelu epilogue needs aux_out");
-  UNIVL_CHECK_ARG(split_k >= 0, "gemm: bad split_k");
-  if (epilogue != EPI_ATOMIC_F32) UNIVL_CHECK_ARG(split_k <= 1, "gemm: split_k>1 needs the atomic epilogue");
-
+namespace {
+struct GemmPlan {
+  int bn, splits, kb_per;
+  bool pair;
+};
+// tile width, split-K factor and kernel variant for a problem — a pure function of the arguments (and the bring-up
+// environment switches), shared by the launcher and by univl_gemm_plan
+int plan_gemm(int M, int N, int Kc, int epilogue, int block_n, int split_k, GemmPlan* plan) {
   const int total_kb = (Kc + BLOCK_K - 1) / BLOCK_K;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   // tile width: widest tile that still yields >= ~1 wave of CTAs on 148 SMs
@@ -484,9 +470,8 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
     }
     if (splits > total_kb) splits = total_kb;
   }
-  int kb_per = (total_kb + splits - 1) / splits;
+  const int kb_per = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per - 1) / kb_per;  // no empty split
-
   // CTA-pair kernel (256 x 256 tiles, half the B traffic per CTA) when the pairs can be kept busy
   bool pair = false;
   if (!use_v1_kernel() && bn == 256 && pair_mode() != 1) {
@@ -494,6 +479,42 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
     pair = pair_mode() == 2 || pair_work >= 60;
   }
   if (force_pair != 0 && !use_v1_kernel() && bn == 256) pair = force_pair > 0;
+  plan->bn = bn; plan->splits = splits; plan->kb_per = kb_per; plan->pair = pair;
+  return UNIVL_OK;
+}
+}  // namespace
+
+// Which kernel univl_gemm_bf16 launches for this problem: 2 = CTA-pair (gemm_tcgen05_2cta_kernel), 1 = single-CTA
+// persistent, 0 = bring-up kernel; negative = error.  Stateless (a function of its arguments): bench.py uses it to
+// attribute per-launch CUDA-event times to the dominant kernel.
+extern "C" int univl_gemm_plan(int M, int N, int Kc, int epilogue, int block_n, int split_k) {
+  GemmPlan plan;
+  if (int rc = plan_gemm(M, N, Kc, epilogue, block_n, split_k, &plan)) return rc;
+  if (use_v1_kernel()) return 0;
+  return plan.pair ? 2 : 1;
+}
+
+extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                               int b_mn_major, int M, int N, int Kc, void* out, long long ldo, int epilogue,
+                               const float* bias, const void* aux_in, long long ld_aux_in, void* aux_out,
+                               long long ld_aux_out, float alpha, int block_n, int split_k, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  UNIVL_CHECK_ARG(M > 0 && N > 0 && Kc > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, Kc);
+  UNIVL_CHECK_ARG(A && B && out, "gemm: null operand");
+  UNIVL_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (got %lld, %lld)",
+                  lda, ldb);
+  UNIVL_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: operands must be 16-byte aligned");
+  UNIVL_CHECK_ARG(epilogue >= 0 && epilogue <= 5, "gemm: unknown epilogue %d", epilogue);
+  if (epilogue == EPI_GELU_BWD_BF16 || epilogue == EPI_ADD_BF16)
+    UNIVL_CHECK_ARG(aux_in != nullptr, "gemm: epilogue %d needs aux_in", epilogue);
+  if (epilogue == EPI_BIAS_GELU_BF16) UNIVL_CHECK_ARG(aux_out != nullptr, "gemm: gelu epilogue needs aux_out");
+  UNIVL_CHECK_ARG(split_k >= 0, "gemm: bad split_k");
+  if (epilogue != EPI_ATOMIC_F32) UNIVL_CHECK_ARG(split_k <= 1, "gemm: split_k>1 needs the atomic epilogue");
+
+  GemmPlan plan;
+  if (int prc = plan_gemm(M, N, Kc, epilogue, block_n, split_k, &plan)) return prc;
+  const int bn = plan.bn, splits = plan.splits, kb_per = plan.kb_per;
+  const bool pair = plan.pair;
 
   CUtensorMap ta, tb;
   int rc;
@@ -543,13 +564,11 @@ extern "C" int univl_gemm_bf16(const void* A, long long lda, int a_mn_major, con
       tx = ta;
     }
     p.tma_epilogue = tma_ok ? 1 : 0;
-    g_last_variant = pair ? 2 : 1;
     if (pair) return dispatch_major_2<256, 5>(amn, bmn, ta, tb, to, tx, p, splits, stream);
     if (bn == 256) return dispatch_major_p<256, 3>(amn, bmn, ta, tb, to, tx, p, splits, stream);
     if (bn == 128) return dispatch_major_p<128, 5>(amn, bmn, ta, tb, to, tx, p, splits, stream);
     return dispatch_major_p<64, 6>(amn, bmn, ta, tb, to, tx, p, splits, stream);
   }
-  g_last_variant = 0;
   if (bn == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, p, splits, stream);
   if (bn == 128) return dispatch_major<128, 3>(amn, bmn, ta, tb, p, splits, stream);
   return dispatch_major<64, 4>(amn, bmn, ta, tb, p, splits, stream);

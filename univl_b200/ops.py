@@ -199,6 +199,7 @@ class _Drop:
         self.pa = float(p_attn) if training else 0.0
         self.seed = arena.seed
         self.arena = arena
+        self.epoch = arena.epoch_host
 
     def stream(self):
         return self.arena.next_stream()
@@ -213,13 +214,12 @@ def attn_block_fwd(xq, xkv, n_seq, Sq, Sk, mask, w, drop):
     sv = {"self": self_attn}
     wqkv = arena.bf16_qkv(w["q"], w["k"], w["v"])
     if self_attn:
-        bqkv = torch.cat((w["bq"], w["bk"], w["bv"]))
-        qkv = linear_fwd(xq, wqkv, bqkv)
+        qkv = linear_fwd(xq, wqkv, rt.packed_bias(w["bq"], w["bk"], w["bv"]))
         q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
         sv["qkv"] = qkv
     else:
         q = linear_fwd(xq, wqkv[:H], w["bq"])
-        kv = linear_fwd(xkv, wqkv[H:], torch.cat((w["bk"], w["bv"])))
+        kv = linear_fwd(xkv, wqkv[H:], rt.packed_bias(w["bk"], w["bv"]))
         k, v = kv[:, :H], kv[:, H:]
         sv["q"], sv["kv"] = q, kv
     sa, sd = drop.stream(), drop.stream()
@@ -228,13 +228,14 @@ def attn_block_fwd(xq, xkv, n_seq, Sq, Sk, mask, w, drop):
     y, mean, rstd = layernorm_fwd(ao, xq, w["gamma"], w["beta"], drop.ph, 1, drop.seed, sd)
     sv.update(xq=xq, xkv=xkv, ctx=ctx, lse=lse, ao=ao, mean=mean, rstd=rstd, sa=sa, sd=sd, n_seq=n_seq, Sq=Sq, Sk=Sk,
               mask=mask, pa=drop.pa, ph=drop.ph, seed=drop.seed, wqkv=wqkv, wo=arena.bf16(w["o"]),
-              gamma=w["gamma"], w=w, sink=GradSink())
+              gamma=w["gamma"], w=w, sink=GradSink(), arena=arena, epoch=drop.epoch)
     return y, sv
 
 
 def attn_block_bwd(dy, dy2, sv, need_dxkv=True):
     """returns dxq, dxkv (None for self-attention: folded into dxq) and the autograd return values per ATT_KEYS"""
     H = sv["xq"].shape[1]
+    sv["arena"].check_epoch(sv["epoch"], max(sv["pa"], sv["ph"]))
     w, sink = sv["w"], sv["sink"]
     dgamma, r_gamma = sink.one(w["gamma"])
     dbeta, r_beta = sink.one(w["beta"])
@@ -283,7 +284,7 @@ def ffn_block_fwd(x, w, drop):
     sd = drop.stream()
     y, mean, rstd = layernorm_fwd(fo, x, w["gamma"], w["beta"], drop.ph, 1, drop.seed, sd)
     sv = dict(x=x, pre=pre, h=h, fo=fo, mean=mean, rstd=rstd, sd=sd, ph=drop.ph, seed=drop.seed, w1=w1, w2=w2,
-              gamma=w["gamma"], w=w, sink=GradSink())
+              gamma=w["gamma"], w=w, sink=GradSink(), arena=arena, epoch=drop.epoch)
     return y, sv
 
 
@@ -291,6 +292,7 @@ def ffn_block_bwd(dy, sv):
     """returns (g_residual, d_x_from_dense) — the caller sums them inside the next LayerNorm backward — and the
     autograd return values per FFN_KEYS"""
     w, sink = sv["w"], sv["sink"]
+    sv["arena"].check_epoch(sv["epoch"], sv["ph"])
     dgamma, r_gamma = sink.one(w["gamma"])
     dbeta, r_beta = sink.one(w["beta"])
     db2, r_b2 = sink.one(w["b2"])

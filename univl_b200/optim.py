@@ -91,7 +91,7 @@ def flatten(model, sink_grads=True):
     """Move `model`'s parameters/gradients into flat buffers; optionally register the gradient sinks."""
     dev = next(model.parameters()).device
     flat = model.__dict__.get("_univl_flat")
-    if flat is None:
+    if flat is None or flat.model is not model:   # (a replica's __dict__ copy carries the original's entry)
         flat = FlatParams(model, dev)
     rt.set_grad_sink(flat if sink_grads else None, model)
     return flat
@@ -164,6 +164,20 @@ class FusedBertAdam(torch.optim.Optimizer):
             self._plist, self._offs = plist, offs
         self.m = torch.zeros_like(self.p)
         self.v = torch.zeros_like(self.p)
+        self._lookup = lookup
+        self.scratch = None
+        self._build_segs()
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._built = True
+
+    def _group_signature(self):
+        return tuple((float(g["lr"]), float(g["weight_decay"]), len(g["params"])) for g in self.param_groups)
+
+    def _build_segs(self):
+        """device chunk table {offset, count, tensor, lr, weight_decay}; rebuilt whenever a param group's lr or
+        weight_decay is edited (or restored by load_state_dict), as torch optimizers honour such edits"""
+        import struct
+        dev = self.p.device
         rows = []
         grp0 = self.param_groups[0]
         for grp in self.param_groups:
@@ -171,9 +185,8 @@ class FusedBertAdam(torch.optim.Optimizer):
                 if grp[key] != grp0[key]:
                     raise ValueError("FusedBertAdam: %s must be the same in every param group" % key)
             for p in grp["params"]:
-                off, n, _ = lookup[id(p)]
+                off, n, _ = self._lookup[id(p)]
                 rows.append((off, n, float(grp["lr"]), float(grp["weight_decay"])))
-        import struct
         chunk = 65536
         parts = []
         for t, (off, n, lr, wd) in enumerate(rows):
@@ -182,13 +195,58 @@ class FusedBertAdam(torch.optim.Optimizer):
         self.segs = torch.frombuffer(bytearray(b"".join(parts)), dtype=torch.uint8).to(dev)
         self.n_chunks = len(parts)
         self.n_tensors = len(rows)
-        self.scratch = torch.zeros(self.n_tensors + 1, dtype=torch.float32, device=dev)
-        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._built = True
+        if self.scratch is None or self.scratch.numel() != self.n_tensors + 1:
+            self.scratch = torch.zeros(self.n_tensors + 1, dtype=torch.float32, device=dev)
+        self._sig = self._group_signature()
+
+    # ---- checkpointing in the reference's layout (modules/optimization.py:121-128: per-parameter
+    # {'step', 'next_m', 'next_v'}; main_pretrain.py:270 saves it, :389 restores it) --------------------------
+    def state_dict(self):
+        if not self._built:
+            return super(FusedBertAdam, self).state_dict()
+        step = int(self.step_dev.item())
+        self.state.clear()
+        if step > 0:
+            for grp in self.param_groups:
+                for p in grp["params"]:
+                    off, n, shape = self._lookup[id(p)]
+                    self.state[p] = {"step": step, "next_m": self.m[off:off + n].view(shape).clone(),
+                                     "next_v": self.v[off:off + n].view(shape).clone()}
+        sd = super(FusedBertAdam, self).state_dict()
+        self.state.clear()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super(FusedBertAdam, self).load_state_dict(state_dict)
+        if not self._built:
+            self._build()
+        step = 0
+        self.m.zero_()
+        self.v.zero_()
+        for p, st in list(self.state.items()):
+            if id(p) not in self._lookup or "next_m" not in st:
+                continue
+            off, n, _ = self._lookup[id(p)]
+            self.m[off:off + n].copy_(st["next_m"].reshape(-1))
+            self.v[off:off + n].copy_(st["next_v"].reshape(-1))
+            step = max(step, int(st["step"]))
+        self.state.clear()
+        self.step_dev.fill_(step)
+        self._build_segs()
 
     def zero_grad(self, set_to_none=False):
-        if self._built:
-            self.g.zero_()
+        """Reference drivers call only `optimizer.zero_grad()` after `optimizer.step()` (main_task_retrieval.py:353,
+        main_pretrain.py:345), so this must clear whatever autograd accumulates into.  Flat layout: the gradient
+        buffer IS every p.grad (views; re-attached if a `model.zero_grad(set_to_none=True)` dropped them).  Compat
+        layout (no `model=`): the per-parameter grads autograd/DDP own are cleared as torch.optim.Optimizer does, in
+        addition to the private flat copy."""
+        if not self._built:
+            return super(FusedBertAdam, self).zero_grad(set_to_none=set_to_none)
+        self.g.zero_()
+        if self.flat is not None:
+            for p, off in zip(self.flat.params, self.flat.offsets):
+                if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + 4 * off:
+                    p.grad = self.g[off:off + p.numel()].view(p.shape)
         else:
             super(FusedBertAdam, self).zero_grad(set_to_none=set_to_none)
 
@@ -214,6 +272,8 @@ class FusedBertAdam(torch.optim.Optimizer):
                         p.grad.copy_(gr)
         if self.flat is None:
             self._gather_grads()
+        if self._group_signature() != self._sig:
+            self._build_segs()
         g0 = self.param_groups[0]
         call("univl_bert_adam_step", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
              None if self.shadow is None else self.shadow.data_ptr(), self.segs.data_ptr(), self.n_chunks,

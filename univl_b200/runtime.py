@@ -57,6 +57,7 @@ class WeightArena:
         # fresh masks while stream ids (position of the dropout site inside a step) stay launch constants.
         self.rng_state = None
         self.stream_counter = 0
+        self.epoch_host = 0   # host mirror of the number of begin_step() calls (detects stale-mask backward passes)
 
     @property
     def seed(self):
@@ -68,8 +69,20 @@ class WeightArena:
 
     def begin_step(self):
         self.stream_counter = 0
+        self.epoch_host += 1
         if self.device is not None:
             call("univl_rng_advance", self.seed)
+
+    def check_epoch(self, epoch, p):
+        """Backward kernels regenerate dropout masks from the device epoch CURRENT when they run.  A second training
+        forward before the first one's backward (loss1 = model(a); loss2 = model(b); (loss1 + loss2).backward(), or
+        a retained graph) would silently regenerate different masks for the first forward: refuse instead."""
+        if p > 0.0 and epoch != self.epoch_host:
+            raise RuntimeError(
+                "univl_b200: backward of a training forward from dropout epoch %d runs at epoch %d — dropout masks "
+                "are regenerated from the device RNG epoch, so each training forward must be followed by its backward "
+                "before the next training forward (or use model.eval() / p = 0 for the extra passes)"
+                % (epoch, self.epoch_host))
 
     # ---- layout -----------------------------------------------------------------------------------------
     def _build(self, device):
@@ -148,8 +161,11 @@ class WeightArena:
 
 
 def arena_of(root):
+    """The arena cached on `root`.  `nn.parallel.replicate` (the reference's util.parallel_apply, util.py:22) builds
+    replicas with `replica.__dict__ = module.__dict__.copy()`, so a replica can carry the ORIGINAL model's arena (its
+    by_id / root refer to the cuda:0 parameters): the cache is valid only when it was built for this very module."""
     a = root.__dict__.get("_univl_arena")
-    if a is None:
+    if a is None or a.root is not root:
         a = WeightArena(root)
         root.__dict__["_univl_arena"] = a
     return a
@@ -199,7 +215,23 @@ def set_grad_sink(flat, model):
 
 def current_sink():
     a = getattr(_tls, "arena", None)
-    return None if a is None else a.root.__dict__.get("_univl_sink")
+    if a is None:
+        return None
+    sink = a.root.__dict__.get("_univl_sink")
+    if sink is not None and sink.model is not a.root:   # a replica inherited the original's registration
+        return None
+    return sink
+
+
+def packed_bias(*bs):
+    """q/k/v projection biases as ONE [3H] vector for the fused QKV projection: a zero-copy view when the three
+    parameters are adjacent in memory (the flat layout of univl_b200.optim.FlatParams), else a concatenated copy."""
+    b0 = bs[0]
+    n = b0.numel()
+    if all(b.numel() == n and b.data_ptr() == b0.data_ptr() + 4 * n * i for i, b in enumerate(bs)):
+        if b0.untyped_storage().nbytes() >= 4 * (b0.storage_offset() + n * len(bs)):
+            return b0.detach().as_strided((n * len(bs),), (1,))
+    return torch.cat(bs)
 
 
 def current():
