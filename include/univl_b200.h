@@ -93,7 +93,19 @@ int univl_attention_bwd(const void* q, long long ldq, const void* k, long long l
                         long long lddq, void* dk, long long lddk, void* dv, long long lddv, const long long* mask_a,
                         const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq, int heads, int Sq,
                         int Sk, int causal, float scale, float p_drop, const unsigned long long* rng_state,
-                        unsigned long long stream_id, float* dbq, float* dbk, float* dbv, void* stream);
+                        unsigned long long stream_id, int rng_layout, float* dbq, float* dbk, float* dbv, void* stream);
+/* ---- fused QKV projection + self-attention, forward (tcgen05 / TMEM / TMA; module_bert.py:171-197 as ONE kernel) ----
+ * ctx[T,H] = merge_heads(dropout(softmax((x Wq^T + bq)(x Wk^T + bk)^T * scale + mask)) (x Wv^T + bv)), T = n_seq * S,
+ * H = heads * 64 = 768.  wqkv: bf16 [3H, H] (query | key | value rows), bias fp32 [3H].  The [T,3H] projections and the
+ * score matrices stay on chip; qkv_out (nullable) additionally receives bf16 q | k | v for the backward pass.  Supported
+ * when univl_fused_qkv_attention_supported(...) == 1 (12 heads, S % 16 == 0, 16 <= S <= 128); masks as above.  Dropout
+ * masks use the row-major layout that univl_attention_bwd regenerates with rng_layout = 1. */
+int univl_fused_qkv_attention_supported(int n_seq, int heads, int S, int H);
+int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const void* wqkv, long long ldw, const float* bias,
+                                  void* qkv_out, long long ld_qkv, void* o, long long ldo, float* lse,
+                                  const long long* mask_a, const long long* mask_b, int Wa, int Fb, int Nb,
+                                  int all_pairs, int n_seq, int heads, int S, int causal, float scale, float p_drop,
+                                  const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
 
 /* ---- utilities ------------------------------------------------------------------------------------------------ */
 int univl_colsum_bf16(const void* x, long long ld, float* out, int rows, int cols, void* stream); /* bias grads */

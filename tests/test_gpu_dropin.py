@@ -81,7 +81,13 @@ def test_reference_retrieval_driver_trains_and_evaluates_on_univl_b200(tmp_path,
     re = drv.load_model(0, args, 1, device, model_file=out)
     for (n, p), (n2, q) in zip(model.named_parameters(), re.named_parameters()):
         assert n == n2 and torch.equal(p.detach(), q.detach()), n
-    # eval path of the driver (all-pairs similarity + retrieval metrics)
+    # eval path of the driver (all-pairs similarity + retrieval metrics).  With n_gpu == 1 the reference hands
+    # compute_metrics a LIST of row blocks (main_task_retrieval.py:443-445: only the n_gpu > 1 branch concatenates) and
+    # metrics.py:9 fails on `-x`; that is the reference's own single-GPU bug, so give it the concatenated matrix.
+    import numpy as np
+    import metrics
+    drv.compute_metrics = lambda sm: metrics.compute_metrics(
+        np.concatenate(tuple(sm), axis=0) if isinstance(sm, list) else sm)
     r1 = drv.eval_epoch(args, ddp_model, torch.utils.data.DataLoader(_Pairs(cfg, 8), batch_size=4), device, 1)
     assert 0.0 <= float(r1) <= 1.0
     if torch.distributed.is_initialized():

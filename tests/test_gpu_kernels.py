@@ -234,6 +234,107 @@ def test_attention_dropout_forward_backward_consistent():
 
 
 # ---------------------------------------------------------------------------------------------------------
+def _fused_inputs(n_seq, S, seed):
+    H = 768
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = _bf(torch.randn(n_seq * S, H, device=DEV, generator=g))
+    w = _bf(torch.randn(3 * H, H, device=DEV, generator=g) * 0.04)
+    b = torch.randn(3 * H, device=DEV, generator=g) * 0.2
+    lens = torch.randint(1, S + 1, (n_seq,), generator=torch.Generator().manual_seed(seed)).to(DEV)
+    mask = (torch.arange(S, device=DEV).unsqueeze(0) < lens.unsqueeze(1)).long()
+    if n_seq > 1:
+        mask[0] = 0   # fully masked sequence: softmax of the raw scores
+    return x, w, b, mask
+
+
+@pytest.mark.parametrize("n_seq,S,causal", [(3, 48, False), (2, 96, False), (5, 48, False), (2, 128, True), (3, 16, False),
+                                            (9, 16, True), (4, 32, False), (3, 64, False), (2, 80, False), (1, 112, False),
+                                            (40, 96, False), (301, 48, False)])
+def test_fused_qkv_attention_fwd_matches_unfused_and_fp32(n_seq, S, causal):
+    """ONE tcgen05 kernel (projection + softmax(QK^T)V) against (a) fp32 PyTorch on the same bf16 inputs and (b) the
+    QKV-GEMM + attention-core pair; packed sequences (S = 16 ... 64), partial last row block, several items per CTA."""
+    H, h = 768, 12
+    assert ops.fused_attention_supported(n_seq, S, H)
+    x, w, b, mask = _fused_inputs(n_seq, S, S + n_seq)
+    spec = ops.MaskSpec(mask, causal=causal)
+    o, lse, qkv = ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    qkv_ref = _bf(x.float() @ w.float().t() + b)                      # the kernel rounds q/k/v to bf16 operand tiles
+    assert (qkv.float() - qkv_ref.float()).abs().max() <= 2.0 ** -7 * max(1.0, float(qkv_ref.float().abs().max()))
+
+    def heads(t):
+        return t.float().view(n_seq, S, h, 64).permute(0, 2, 1, 3)
+    qf, kf, vf = heads(qkv_ref[:, :H]), heads(qkv_ref[:, H:2 * H]), heads(qkv_ref[:, 2 * H:])
+    add = (1.0 - mask.float()).view(n_seq, 1, 1, S) * -10000.0
+    if causal:
+        fut = torch.triu(torch.ones(S, S, device=DEV), diagonal=1).view(1, 1, S, S)
+        add = ((1.0 - mask.float()).view(n_seq, 1, 1, S) + fut).gt(0).float() * -10000.0
+    sc = torch.matmul(qf, kf.transpose(-1, -2)) / 8.0 + add
+    ref = torch.matmul(torch.softmax(sc, -1), vf).permute(0, 2, 1, 3).reshape(n_seq * S, H)
+    assert (o.float() - ref).abs().max() <= 3e-2
+    lse_ref = torch.logsumexp(sc, -1).reshape(-1)
+    assert (lse - lse_ref).abs().max() <= 2e-2 + 2e-3 * float(lse_ref.abs().max())
+    # the unfused pair on the kernel's own q/k/v
+    o2, lse2 = ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], n_seq, S, S, spec)
+    assert (o.float() - o2.float()).abs().max() <= 2e-2
+    assert (lse - lse2).abs().max() <= 2e-3 * max(1.0, float(lse2.abs().max()))
+    # no q/k/v copy requested: same context
+    o3, _, none = ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec, save_qkv=False)
+    assert none is None and torch.equal(o3, o)
+
+
+def test_fused_qkv_attention_all_pairs_masks():
+    Na, Nb, W, F, H = 3, 4, 16, 32, 768
+    S = W + F
+    x, w, b, _ = _fused_inputs(Na * Nb, S, 11)
+    ma = (torch.arange(W, device=DEV).unsqueeze(0) < torch.tensor([5, 16, 1], device=DEV).unsqueeze(1)).long()
+    mb = (torch.arange(F, device=DEV).unsqueeze(0) < torch.tensor([3, 32, 9, 20], device=DEV).unsqueeze(1)).long()
+    o, _, _ = ops.fused_qkv_attention_fwd(x, w, b, Na * Nb, S, ops.MaskSpec(ma, mb, all_pairs=True))
+    full = torch.cat([ma.unsqueeze(1).expand(Na, Nb, W), mb.unsqueeze(0).expand(Na, Nb, F)], -1).reshape(Na * Nb, S)
+    o2, _, _ = ops.fused_qkv_attention_fwd(x, w, b, Na * Nb, S, ops.MaskSpec(full))
+    assert torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("n_seq,S", [(3, 48), (2, 96), (2, 128)])
+def test_fused_qkv_attention_dropout_pairs_with_backward(n_seq, S):
+    """dropout masks drawn by the fused forward (row-major layout) are regenerated by attention_bwd(rng_layout=1)"""
+    H, p = 768, 0.25
+    x, w, b, mask = _fused_inputs(n_seq, S, 21)
+    mask[:] = 1
+    spec = ops.MaskSpec(mask)
+    o0, _, _ = ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec)
+    o1, lse, qkv = ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec, p=p, seed=RNG.data_ptr(), stream=3)
+    o2, _, _ = ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec, p=p, seed=RNG.data_ptr(), stream=3)
+    assert torch.equal(o1, o2) and not torch.equal(o0, o1)
+    acc = torch.zeros_like(o0, dtype=torch.float32)
+    n = 48
+    for s in range(n):
+        acc += ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec, p=p, seed=RNG.data_ptr(), stream=100 + s)[0].float()
+    assert (acc / n - o0.float()).abs().mean() <= 3e-2
+    # O is linear in V = x Wv^T + bv: a step along a bias direction d moves every V row by d, so
+    # <dO, O(bv + e d) - O(bv)> / e = <colsum(dV), d>, exact up to bf16 rounding — IF backward regenerates the same mask
+    g = torch.Generator(device=DEV).manual_seed(5)
+    d_o = _bf(torch.randn(n_seq * S, H, device=DEV, generator=g))
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o1, lse, d_o, dqkv[:, :H], dqkv[:, H:2 * H],
+                      dqkv[:, 2 * H:], n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=3, rng_layout=1)
+    d = torch.randn(H, device=DEV, generator=g)
+    eps = 0.5
+    b2 = b.clone()
+    b2[2 * H:] += eps * d
+    op, _, _ = ops.fused_qkv_attention_fwd(x, w, b2, n_seq, S, spec, p=p, seed=RNG.data_ptr(), stream=3)
+    lhs = ((op.float() - o1.float()) * d_o.float()).sum() / eps
+    rhs = (dqkv[:, 2 * H:].float().sum(0) * d).sum()
+    assert abs(float(lhs - rhs)) <= 3e-2 * abs(float(rhs)) + 1.0
+    # and the wrong layout must NOT satisfy it (guards against the test passing vacuously)
+    dq_bad = torch.empty_like(qkv)
+    ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o1, lse, d_o, dq_bad[:, :H], dq_bad[:, H:2 * H],
+                      dq_bad[:, 2 * H:], n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=3, rng_layout=0)
+    assert not torch.equal(dq_bad, dqkv)
+
+
+# ---------------------------------------------------------------------------------------------------------
 def test_embeddings_text_and_sources():
     n, S, H, V = 3, 20, 768, 1000
     g = torch.Generator(device=DEV).manual_seed(7)

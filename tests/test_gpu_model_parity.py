@@ -9,11 +9,15 @@ Stated tolerances (bf16 activations, fp32 accumulation / statistics / losses; th
          cross-entropy losses over the vocabulary / frames (caption, pretrain-II):            |d| <= 2e-3 * |loss|
          MIL-NCE on UN-normalised dot products (use_mil): |d| <= 2^-8 * max|sim| — the logits are only resolved to
          bf16 precision relative to their magnitude (~25 here)
-  hidden states   relative Frobenius error <= (layers + 1) * 2^-9: one worst-case bf16 round-to-nearest error (2^-9
-                  relative) per layer of the stack, accumulated linearly (+1 for the embedding).  The expected value under
-                  independent roundings is sqrt(7 roundings x layers) * 2^-9 / sqrt(3) = 1.0e-2 for the 12-layer text
-                  stack, so the bound leaves ~2x; the achieved margins are written to gpurun_out/parity_margins.json and
-                  listed in DESIGN.md.  Worst single element: 0.1 absolute on values of magnitude 2-4 (~6 bf16 ulps).
+  hidden states   relative Frobenius error <= 2 * sqrt(7 * (layers + 1)) * 2^-9 / sqrt(3).  Derivation: every layer
+                  stores 7 bf16 tensors on the path to its output (qkv, context, attention-out, LN1-out, FFN
+                  pre-activation / activation, FFN-out, LN2-out; +1 "layer" for the embedding / input projection); a
+                  round-to-nearest bf16 store has relative error uniform in [-2^-9, 2^-9], RMS 2^-9 / sqrt(3); the
+                  roundings are independent, so the expected relative Frobenius error of an L-layer stack is
+                  sqrt(7 (L + 1)) * 2^-9 / sqrt(3)  (2 layers 5.2e-3, 6 layers 7.9e-3, 12 layers 1.08e-2); the bound is
+                  twice that.  Measured / expected is 1.1-1.2 (LayerNorm gains of the stress weights); the achieved
+                  margins are written to gpurun_out/parity_margins.json and listed in DESIGN.md.  Worst single element:
+                  0.1 absolute on values of magnitude 2-4 (~6 bf16 ulps).
   gradients       per tensor ||g - g_oracle|| <= 0.10 * max(||g_oracle||, 0.05 * largest gradient norm) and, for tensors
                   above that floor, norm within 6 %.  The floor exists because some gradients are mathematically (key
                   biases: softmax shift invariance) or numerically (q/k weights of deep layers once attention has
@@ -116,12 +120,12 @@ def test_loss_hidden_and_grads_match_reference(name):
 
     o_loss, parts, o_grads = run_oracle(cfg, batch, sd=sd, backward=True)
     assert abs(got - float(o_loss)) <= tol
-    # hidden states after an L-layer bf16 stack against the fp32 reference algorithm: derived bound (L + 1) * 2^-9 on the
-    # relative Frobenius error (see the module docstring); worst single element ~6 bf16 ulps of |x| = 2..4.
+    # hidden states after an L-layer bf16 stack against the fp32 reference algorithm: derived bound on the relative
+    # Frobenius error (see the module docstring); worst single element ~6 bf16 ulps of |x| = 2..4.
     for tag, ours, ref, layers in (("seq", seq, parts["sequence_output"].detach(), cfg.text_num_hidden_layers),
                                    ("vis", vis, parts["visual_output"].detach(), cfg.visual_num_hidden_layers)):
         rel = float((ours - ref).norm() / ref.norm())
-        bound = (layers + 1) * 2.0 ** -9
+        bound = 2.0 * (7.0 * (layers + 1)) ** 0.5 * 2.0 ** -9 / 3.0 ** 0.5
         _record(name, **{tag + "_rel_fro": rel, tag + "_bound": bound, tag + "_max_abs": float((ours - ref).abs().max())})
         assert rel <= bound, (tag, rel, bound)
         assert float((ours - ref).abs().max()) <= 1e-1

@@ -45,6 +45,7 @@ struct AttnParams {
   bf16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
   int share_tiles;  // backward: 1 = query-major pass shares P_drop / dS with the key-major pass through smem
+  int rng_rowmajor; // backward: dropout layout of the fused QKV+attention forward kernel (fused_attn.cu), see tile_rng_rowmajor
   float *dbq, *dbk, *dbv;  // backward, optional: projection-bias gradients += column sums of dq / dk / dv  [heads*64]
 };
 
@@ -138,6 +139,31 @@ __device__ __forceinline__ void mma_p_z(const uint32_t (&pa)[4], const bf16* Z, 
 __device__ __forceinline__ uint4 tile_rng(const AttnParams& p, long long bh, int qb, int kb, int nQb, int nKb,
                                           int lane_f) {
   return philox4x32(p.seed, p.stream, (uint64_t)(((bh * nQb + qb) * (long long)nKb + kb) * 32 + lane_f));
+}
+
+// Row-major dropout layout (written by fused_attn.cu's forward): element (bh, query i, key j) is 16-bit word (j & 7) of
+// Philox(seed, stream, (bh * Sq + i) * (Sk / 8) + j / 8).  In the mma fragment a thread (g, t) holds, of the 16 x 16 tile
+// (q0, kb), rows i0 = q0 + g and i1 = i0 + 8 and keys kb*16 + nb*8 + 2t + {0, 1}: the two keys are the halves of 32-bit
+// word t of the (row, nb) call.  The four lanes of a quad share the four calls (row i0 / i1) x (nb 0 / 1): lane t computes
+// call c = t and the quad exchanges words with three XOR shuffles.  Returns w[rsel * 2 + nb] = word t of that call.
+__device__ __forceinline__ void tile_rng_rowmajor(const AttnParams& p, long long bh, int q0, int kb, int lane,
+                                                  uint32_t (&w)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  const int row = q0 + g + ((t >> 1) ? 8 : 0);
+  const uint4 r = philox4x32(p.seed, p.stream,
+                             (uint64_t)(bh * p.Sq + row) * (uint64_t)(p.Sk >> 3) + (uint64_t)(kb * 2 + (t & 1)));
+  uint32_t got[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int want = t ^ k;  // component the partner lane (t ^ k) needs from this lane's call
+    const uint32_t send = want == 0 ? r.x : want == 1 ? r.y : want == 2 ? r.z : r.w;
+    got[k] = __shfl_xor_sync(0xffffffffu, send, k);  // = word t of call (t ^ k)
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k = c ^ t;
+    w[c] = k == 0 ? got[0] : k == 1 ? got[1] : k == 2 ? got[2] : got[3];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -423,7 +449,11 @@ __device__ __forceinline__ void bwd_dq_task(const AttnParams& p, const BwdSmem& 
     mma_a_yT(qa, sK, j0, lane, s);
     mma_a_yT(da, sV, j0, lane, dp);
     uint4 rnd = make_uint4(0, 0, 0, 0);
-    if (p.drop_on) rnd = tile_rng(p, bh, q0 >> 4, j0 >> 4, Sq16 >> 4, Sk16 >> 4, lane);
+    uint32_t rw[4] = {0, 0, 0, 0};
+    if (p.drop_on) {
+      if (p.rng_rowmajor) tile_rng_rowmajor(p, bh, q0, j0 >> 4, lane, rw);
+      else rnd = tile_rng(p, bh, q0 >> 4, j0 >> 4, Sq16 >> 4, Sk16 >> 4, lane);
+    }
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
       const int jb = j0 + nb * 8 + 2 * t;
@@ -441,8 +471,11 @@ __device__ __forceinline__ void bwd_dq_task(const AttnParams& p, const BwdSmem& 
         float g0 = dp[nb][e], g1 = dp[nb][2 + e];
         float pk0 = p0, pk1 = p1;
         if (p.drop_on) {
-          const bool kp0 = philox_u16(rnd, e | (nb << 2)) < p.drop_threshold;
-          const bool kp1 = philox_u16(rnd, e | 2 | (nb << 2)) < p.drop_threshold;
+          const uint32_t u0 = p.rng_rowmajor ? (e ? rw[nb] >> 16 : rw[nb] & 0xFFFFu) : philox_u16(rnd, e | (nb << 2));
+          const uint32_t u1 = p.rng_rowmajor ? (e ? rw[2 + nb] >> 16 : rw[2 + nb] & 0xFFFFu)
+                                             : philox_u16(rnd, e | 2 | (nb << 2));
+          const bool kp0 = u0 < p.drop_threshold;
+          const bool kp1 = u1 < p.drop_threshold;
           g0 = kp0 ? g0 * p.drop_scale : 0.f;
           g1 = kp1 ? g1 * p.drop_scale : 0.f;
           pk0 = kp0 ? p0 * p.drop_scale : 0.f;
@@ -776,7 +809,7 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
                                    long long lddv, const long long* mask_a, const long long* mask_b, int Wa, int Fb,
                                    int Nb, int all_pairs, int n_seq, int heads, int Sq, int Sk, int causal, float scale,
                                    float p_drop, const unsigned long long* rng_state, unsigned long long stream_id,
-                                   float* dbq, float* dbk, float* dbv, void* stream) {
+                                   int rng_layout, float* dbq, float* dbk, float* dbv, void* stream) {
   AttnParams p = {};
   if (int rc = fill_common(p, q, ldq, k, ldk, v, ldv, mask_a, mask_b, Wa, Fb, Nb, all_pairs, n_seq, heads, Sq, Sk,
                            causal, scale, p_drop, rng_state, stream_id))
@@ -795,6 +828,12 @@ extern "C" int univl_attention_bwd(const void* q, long long ldq, const void* k, 
   const int Sq16 = (Sq + 15) & ~15, Sk16 = (Sk + 15) & ~15;
   size_t smem = (size_t)(2 * Sq16 + 2 * Sk16) * LDS * 2 + (size_t)(Sk16 + 2 * Sq16 + (Sq16 / 16 + 2 * (Sk16 / 16)) * 64) * 4;
   p.share_tiles = (Sq16 <= 128 && Sk16 <= 128) ? 1 : 0;
+  // rng_layout 1: masks were drawn by the fused QKV+attention forward kernel (row-major layout).  That kernel only runs
+  // self-attention with S % 16 == 0, S <= 128, where the backward is always in tile-sharing mode.
+  UNIVL_CHECK_ARG(rng_layout == 0 || rng_layout == 1, "attention_bwd: unknown rng_layout %d", rng_layout);
+  UNIVL_CHECK_ARG(rng_layout == 0 || (p.share_tiles && Sq == Sk && (Sk % 16) == 0),
+                  "attention_bwd: rng_layout 1 needs self-attention with S %% 16 == 0 and S <= 128");
+  p.rng_rowmajor = rng_layout;
   if (p.share_tiles) smem += (size_t)2 * Sq16 * (Sk16 + 8) * 2;
   cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "attention_bwd smem attribute: %s", cudaGetErrorString(e));

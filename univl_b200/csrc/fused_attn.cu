@@ -1,0 +1,516 @@
+// univl_b200 — fused QKV-projection + multi-head self-attention, forward, on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Reference op sequence replaced (modules/module_bert.py:171-197 = module_visual.py:155-181 = module_cross.py:162-188;
+// decoder self-attention module_decoder.py:220-247 with the causal mask of :385-396):
+//     q,k,v = x Wq^T + bq, x Wk^T + bk, x Wv^T + bv ;  scores = q k^T / 8 + mask ;  P = dropout(softmax(scores)) ;
+//     ctx = P v, heads merged.
+// ONE kernel: the [T,2304] q/k/v tensor and the [B,12,S,S] scores never exist in HBM (q/k/v are optionally ALSO
+// written out for the backward pass in training).
+//
+// Work item = (row block, head).  A row block is G = floor(128 / S) whole sequences = RB = G*S <= 128 consecutive
+// token rows (S = 48 -> 96 rows, S = 96 -> 96, S = 128 -> 128); a CTA walks a contiguous range of items, heads
+// fastest, so its x rows stay in L2 for the 12 heads.  Per item:
+//   1. projection   acc[128, 192] = x[128 rows, 768] . Wqkv_h[192, 768]^T      12 k-blocks x 4 tcgen05.mma (M128 N192 K16),
+//                   x and the three 64-row weight slices arrive by TMA into a 3-stage mbarrier ring
+//   2. drain        TMEM -> registers (+bias) -> bf16 -> Q, K, V shared-memory tiles in the 128B-swizzled UMMA operand
+//                   layout (one physical layout serves Q as K-major A, K as K-major B, V as MN-major B)
+//   3. S = Q K^T    4 tcgen05.mma (M128, N = RB, K16) into TMEM
+//   4. softmax      one thread per query row: tcgen05.ld, scale + additive mask (-10000 padding / causal, block-diagonal
+//                   across the packed sequences), exact online max/sum, Philox dropout, P (bf16) -> shared memory as
+//                   the K-major A operand, log-sum-exp -> HBM
+//   5. O = P V      RB/16 tcgen05.mma (M128 N64 K16) into TMEM, drained to the merged-head context rows in HBM.
+// TMEM (512 columns) is split in two halves that alternate between consecutive items: while the CUDA cores drain /
+// softmax item j in one half, the tensor pipe runs the projection of item j+1 in the other; the single MMA-issuing
+// thread interleaves the short S / PV products of item j between projection k-blocks of item j+1 as soon as their
+// operands are ready (mbarrier polling), so the tensor pipe only idles when it is genuinely starved.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain (TMEM lane quarter = warp & 3),
+// warps 6-9 softmax.  All synchronisation is mbarrier-based (tcgen05.commit on the MMA side).
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace univl {
+
+constexpr int FA_THREADS = 320;
+constexpr int FA_STAGES = 3;
+constexpr int FA_KB = 12;                       // 768 / 64 k-blocks
+constexpr int FA_X_BYTES = 128 * 64 * 2;        // 16 KB: x rows of one k-block
+constexpr int FA_W_BYTES = 192 * 64 * 2;        // 24 KB: q/k/v weight rows of one head, one k-block
+constexpr int FA_STAGE_BYTES = FA_X_BYTES + FA_W_BYTES;
+constexpr int FA_TILE_BYTES = 128 * 128;        // one [128 rows][64 bf16] operand tile
+constexpr int FA_OFF_Q = FA_STAGES * FA_STAGE_BYTES;
+constexpr int FA_OFF_K = FA_OFF_Q + FA_TILE_BYTES;
+constexpr int FA_OFF_V = FA_OFF_K + FA_TILE_BYTES;
+constexpr int FA_OFF_P = FA_OFF_V + FA_TILE_BYTES;            // two 64-key atoms
+constexpr int FA_OFF_MADD = FA_OFF_P + 2 * FA_TILE_BYTES;     // 128 floats
+constexpr int FA_OFF_BAR = FA_OFF_MADD + 512;
+// full[3] empty[3] acc_full[2] s_full[2] p_ready[2] pv_done[2] half_free[2] qkv_ready[1]
+constexpr int FA_NUM_BARS = 2 * FA_STAGES + 11;
+constexpr int FA_SMEM_BYTES = FA_OFF_BAR + FA_NUM_BARS * 8 + 16 + 1024;
+constexpr int FA_HALF_COLS = 256;
+constexpr int FA_O_COL = 128;                   // O accumulator columns inside a half
+
+struct FusedAttnParams {
+  int T, S, G, RB, n_seq, heads, n_blocks;
+  const float* bias;          // [3 * heads * 64]
+  bf16* o;
+  long long ldo;
+  float* lse;                 // [n_seq, heads, S]
+  const long long* mask_a;
+  const long long* mask_b;
+  int Wa, Fb, Nb, all_pairs, causal;
+  float scale;
+  int drop_on;
+  uint32_t drop_threshold;
+  float drop_scale;
+  const unsigned long long* rng;
+  uint64_t stream;
+  int store_qkv;
+};
+
+__device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity, bool blocking) {
+  if (!blocking) return mbar_try_wait(bar, parity) != 0;
+  mbar_wait(bar, parity);
+  return true;
+}
+
+// items [begin, end) of this CTA: contiguous ranges, the first (total % grid) CTAs take one more
+__device__ __forceinline__ void fa_item_range(int total, int& begin, int& end) {
+  const int per = total / (int)gridDim.x, rem = total % (int)gridDim.x;
+  const int b = (int)blockIdx.x;
+  begin = b * per + min(b, rem);
+  end = begin + per + (b < rem ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                               const __grid_constant__ CUtensorMap tmap_qkv, const FusedAttnParams p_in) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FA_OFF_BAR);
+  uint64_t* empty_bar = full_bar + FA_STAGES;
+  uint64_t* acc_full = empty_bar + FA_STAGES;   // [2] projection accumulators complete      (MMA commit -> drain)
+  uint64_t* s_full = acc_full + 2;              // [2] S = Q K^T complete                    (MMA commit -> softmax)
+  uint64_t* p_ready = s_full + 2;               // [2] P in shared memory, S reads finished   (softmax -> MMA)
+  uint64_t* pv_done = p_ready + 2;              // [2] O complete; Q/K/V/P tiles free         (MMA commit -> drain)
+  uint64_t* half_free = pv_done + 2;            // [2] O drained: TMEM half reusable          (drain -> MMA)
+  uint64_t* qkv_ready = half_free + 2;          // [1] Q/K/V tiles written                    (drain -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qkv_ready + 1);
+  float* madd = reinterpret_cast<float*>(smem + FA_OFF_MADD);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  FusedAttnParams p = p_in;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    if (p.store_qkv) tma_prefetch_desc(&tmap_qkv);
+    for (int s = 0; s < FA_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_ready[b], 4);    // one arrival per softmax warp
+      mbar_init(&pv_done[b], 1);
+      mbar_init(&half_free[b], 4);  // one arrival per drain warp
+    }
+    mbar_init(qkv_ready, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  int item_begin, item_end;
+  fa_item_range(p.n_blocks * p.heads, item_begin, item_end);
+  const int n_items = item_end - item_begin;
+  const int NK = p.RB;  // keys per block (S % 16 == 0, so RB is a multiple of 16)
+
+  if (warp == 0) {
+    // ------------------------------------------ TMA producer ------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int j = 0; j < n_items; ++j) {
+        const int w = item_begin + j;
+        const int rb = w / p.heads, h = w - rb * p.heads;
+        const int r0 = rb * p.RB;
+        for (int kb = 0; kb < FA_KB; ++kb, ++it) {
+          const int s = it % FA_STAGES;
+          const uint32_t ph = (it / FA_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sx = smem + s * FA_STAGE_BYTES;
+          uint8_t* sw = sx + FA_X_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], FA_STAGE_BYTES);
+          tma_load_2d(sx, &tmap_x, &full_bar[s], kb * 64, r0);  // rows >= T arrive as zeros
+#pragma unroll
+          for (int m = 0; m < 3; ++m)  // q / k / v weight rows of head h: rows m*H + h*64 of Wqkv[3H, 768]
+            tma_load_2d(sw + m * 8192, &tmap_w, &full_bar[s], kb * 64, m * p.heads * 64 + h * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------ MMA issuer --------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_proj = make_idesc_bf16(128, 192, false, false);
+      const uint32_t idesc_s = make_idesc_bf16(128, NK, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+      const uint32_t sQ = smem_u32(smem + FA_OFF_Q), sK = smem_u32(smem + FA_OFF_K);
+      const uint32_t sV = smem_u32(smem + FA_OFF_V), sP = smem_u32(smem + FA_OFF_P);
+      int core_j = 0, core_stage = 0;  // next S (stage 0) / PV (stage 1) product to issue, in item order
+      auto try_core = [&](bool blocking) -> bool {
+        if (core_j >= n_items) return false;
+        const int b = core_j & 1;
+        const uint32_t half = tmem_base + b * FA_HALF_COLS;
+        if (core_stage == 0) {
+          if (!mbar_poll(qkv_ready, core_j & 1, blocking)) return false;
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(half, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                      idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[b]);
+          core_stage = 1;
+        } else {
+          if (!mbar_poll(&p_ready[b], (core_j >> 1) & 1, blocking)) return false;
+          tc_fence_after_sync();
+          for (int kk = 0; kk < NK / 16; ++kk)  // contraction over keys: P K-major (64-key atoms), V MN-major
+            umma_bf16(half + FA_O_COL, make_smem_desc_sw128(sP + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(sV + kk * 2048, FA_TILE_BYTES, 1024), idesc_pv, kk > 0 ? 1u : 0u);
+          umma_commit(&pv_done[b]);
+          core_stage = 0;
+          ++core_j;
+        }
+        return true;
+      };
+      auto wait_serving = [&](uint64_t* bar, uint32_t parity) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(bar, parity)) {
+          try_core(false);
+          if (++spins > (1u << 24)) {
+            printf("univl: fused attention MMA wait timed out (block %d)\n", blockIdx.x);
+            __trap();
+          }
+        }
+      };
+      uint32_t it = 0;
+      for (int j = 0; j < n_items; ++j) {
+        const int b = j & 1;
+        wait_serving(&half_free[b], (((uint32_t)j >> 1) & 1) ^ 1);  // O of item j-2 drained out of this half
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + b * FA_HALF_COLS;
+        for (int kb = 0; kb < FA_KB; ++kb, ++it) {
+          try_core(false);
+          const int s = it % FA_STAGES;
+          const uint32_t ph = (it / FA_STAGES) & 1;
+          wait_serving(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t sx = smem_u32(smem + s * FA_STAGE_BYTES);
+          const uint32_t sw = sx + FA_X_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, make_smem_desc_sw128(sx + k * 32, 16, 1024), make_smem_desc_sw128(sw + k * 32, 16, 1024),
+                      idesc_proj, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+      while (core_j < n_items) try_core(true);
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------ drain warps -------------------------------------------
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int row = q * 32 + lane;          // tile row this thread owns
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int jj = 0; jj <= n_items; ++jj) {
+      if (jj >= 1) {
+        // ---- O of item jj-1 -> merged-head context rows ----
+        const int j = jj - 1, b = j & 1;
+        const int w = item_begin + j;
+        const int rb = w / p.heads, h = w - rb * p.heads;
+        mbar_wait(&pv_done[b], ((uint32_t)j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t t_o = tmem_base + b * FA_HALF_COLS + FA_O_COL + lane_base;
+        uint32_t r[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(t_o + c * 16, r[c]);
+        tmem_ld_wait();
+        const long long tok = (long long)rb * p.RB + row;
+        if (row < p.RB && tok < p.T) {
+          bf16* orow = p.o + tok * p.ldo + h * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u0, u1;
+            u0.x = pack_bf16x2(__uint_as_float(r[c][0]), __uint_as_float(r[c][1]));
+            u0.y = pack_bf16x2(__uint_as_float(r[c][2]), __uint_as_float(r[c][3]));
+            u0.z = pack_bf16x2(__uint_as_float(r[c][4]), __uint_as_float(r[c][5]));
+            u0.w = pack_bf16x2(__uint_as_float(r[c][6]), __uint_as_float(r[c][7]));
+            u1.x = pack_bf16x2(__uint_as_float(r[c][8]), __uint_as_float(r[c][9]));
+            u1.y = pack_bf16x2(__uint_as_float(r[c][10]), __uint_as_float(r[c][11]));
+            u1.z = pack_bf16x2(__uint_as_float(r[c][12]), __uint_as_float(r[c][13]));
+            u1.w = pack_bf16x2(__uint_as_float(r[c][14]), __uint_as_float(r[c][15]));
+            *reinterpret_cast<uint4*>(orow + c * 16) = u0;
+            *reinterpret_cast<uint4*>(orow + c * 16 + 8) = u1;
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&half_free[b]);
+      }
+      if (jj < n_items) {
+        // ---- projection accumulators of item jj -> Q / K / V operand tiles (Q/K/V/P of item jj-1 are free: pv_done) ----
+        const int j = jj, b = j & 1;
+        const int w = item_begin + j;
+        const int rb = w / p.heads, h = w - rb * p.heads;
+        mbar_wait(&acc_full[b], ((uint32_t)j >> 1) & 1);
+        tc_fence_after_sync();
+        if (p.store_qkv && jj >= 1) {
+          if (lane == 0) bulk_wait_read<0>();  // the bulk stores of item jj-1 have read this warp's tile rows
+          __syncwarp();
+        }
+        const uint32_t t_acc = tmem_base + b * FA_HALF_COLS + lane_base;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          uint32_t r[4][16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(t_acc + m * 64 + c * 16, r[c]);
+          tmem_ld_wait();
+          const float* bias = p.bias + m * p.heads * 64 + h * 64;
+          uint8_t* trow = smem + FA_OFF_Q + m * FA_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c * 16 + e));
+              v[e] = __uint_as_float(r[c][e]) + bb.x;
+              v[e + 1] = __uint_as_float(r[c][e + 1]) + bb.y;
+              v[e + 2] = __uint_as_float(r[c][e + 2]) + bb.z;
+              v[e + 3] = __uint_as_float(r[c][e + 3]) + bb.w;
+            }
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              uint4 u;
+              u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+              u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+              u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+              u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+              const int chunk = c * 2 + g8;  // 16-byte chunk inside the 128-byte row; XOR swizzle = TMA/UMMA 128B swizzle
+              *reinterpret_cast<uint4*>(trow + ((chunk ^ (row & 7)) << 4)) = u;
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core and the bulk-copy engine
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.store_qkv && q * 32 < p.RB) {
+            const int r0 = rb * p.RB + q * 32;
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+              tma_store_2d(&tmap_qkv, smem + FA_OFF_Q + m * FA_TILE_BYTES + q * 4096, m * p.heads * 64 + h * 64, r0);
+            bulk_commit();
+          }
+          mbar_arrive(qkv_ready);
+        }
+      }
+    }
+    if (p.store_qkv && lane == 0) bulk_wait_read<0>();
+  } else {
+    // ------------------------------------------ softmax warps -----------------------------------------
+    if (p.drop_on && p.rng != nullptr) {
+      // device-side {seed, epoch}: fresh masks on every CUDA-graph replay (see common.cuh / univl_rng_advance)
+    }
+    const uint64_t seed = (p.drop_on && p.rng != nullptr) ? p.rng[0] : 0ull;
+    const uint64_t stream = p.stream + ((p.drop_on && p.rng != nullptr) ? (p.rng[1] << 20) : 0ull);
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int g = row / p.S;                 // packed sequence this query row belongs to
+    const int c0 = g * p.S;                  // first key column of that sequence
+    const int qpos = row - c0;
+    const float sl2 = p.scale * 1.44269504088896340736f;
+    const float neg_big = -10000.0f * 1.44269504088896340736f;
+    int cur_rb = -1;
+    for (int j = 0; j < n_items; ++j) {
+      const int b = j & 1;
+      const int w = item_begin + j;
+      const int rb = w / p.heads, h = w - rb * p.heads;
+      if (rb != cur_rb) {
+        // additive key mask of this row block (log2 domain): 0 / -10000 per key column; shared by the 12 heads
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // every softmax warp is done with the previous block's mask
+        float m = 0.f;
+        if (row < NK) {
+          const long long seq = (long long)rb * p.G + g;
+          long long mv = 1;
+          if (p.mask_a != nullptr && seq < p.n_seq) {
+            const long long mi = p.all_pairs ? seq / p.Nb : seq, mj = p.all_pairs ? seq % p.Nb : seq;
+            if (qpos < p.Wa) mv = p.mask_a[mi * p.Wa + qpos];
+            else if (p.mask_b != nullptr) mv = p.mask_b[mj * p.Fb + (qpos - p.Wa)];
+          }
+          m = mv != 0 ? 0.f : neg_big;
+        }
+        madd[row] = m;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_rb = rb;
+      }
+      mbar_wait(&s_full[b], ((uint32_t)j >> 1) & 1);
+      tc_fence_after_sync();
+      const long long seq = (long long)rb * p.G + g;
+      const bool valid = row < p.RB && seq < p.n_seq;
+      const uint32_t t_s = tmem_base + b * FA_HALF_COLS + lane_base;
+      uint8_t* prow = smem + FA_OFF_P + row * 128;
+      const int sw = row & 7;
+      float mx = -INFINITY, l = 0.f;
+      if (valid) {
+        for (int c = 0; c < p.S; c += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_s + c0 + c, r);
+          tmem_ld_wait();
+          float t[16];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a = madd[c0 + c + e];
+            if (p.causal && (c + e) > qpos && a == 0.f) a = neg_big;
+            t[e] = fmaf(__uint_as_float(r[e]), sl2, a);
+            cm = fmaxf(cm, t[e]);
+          }
+          const float nm = fmaxf(mx, cm);
+          float acc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc += ex2_approx(t[e] - nm);
+          l = l * ex2_approx(mx - nm) + acc;
+          mx = nm;
+        }
+      }
+      const float inv = valid ? (p.drop_on ? p.drop_scale : 1.0f) / l : 0.f;
+      const long long bh = seq * p.heads + h;
+      // P row: zeros outside the own sequence (block-diagonal) and for rows that carry no query
+      for (int c = 0; c < NK; c += 16) {
+        uint4 u0 = make_uint4(0, 0, 0, 0), u1 = make_uint4(0, 0, 0, 0);
+        if (valid && c >= c0 && c < c0 + p.S) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_s + c, r);
+          tmem_ld_wait();
+          const int kc = c - c0;  // key position inside the sequence (multiple of 16)
+          float pr[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a = madd[c + e];
+            if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
+            pr[e] = ex2_approx(fmaf(__uint_as_float(r[e]), sl2, a) - mx) * inv;
+          }
+          if (p.drop_on) {
+            // row-major dropout layout: element (bh, query, key) = 16-bit word (key & 7) of
+            // Philox(seed, stream, (bh * S + query) * (S / 8) + key / 8)
+            const uint64_t base = ((uint64_t)bh * p.S + qpos) * (uint64_t)(p.S >> 3) + (uint64_t)(kc >> 3);
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              const uint4 rnd = philox4x32(seed, stream, base + g8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (philox_u16(rnd, e) >= p.drop_threshold) pr[g8 * 8 + e] = 0.f;
+            }
+          }
+          u0.x = pack_bf16x2(pr[0], pr[1]);   u0.y = pack_bf16x2(pr[2], pr[3]);
+          u0.z = pack_bf16x2(pr[4], pr[5]);   u0.w = pack_bf16x2(pr[6], pr[7]);
+          u1.x = pack_bf16x2(pr[8], pr[9]);   u1.y = pack_bf16x2(pr[10], pr[11]);
+          u1.z = pack_bf16x2(pr[12], pr[13]); u1.w = pack_bf16x2(pr[14], pr[15]);
+        }
+        const int atom = c >> 6, chunk = (c & 63) >> 3;
+        *reinterpret_cast<uint4*>(prow + atom * FA_TILE_BYTES + ((chunk ^ sw) << 4)) = u0;
+        *reinterpret_cast<uint4*>(prow + atom * FA_TILE_BYTES + (((chunk + 1) ^ sw) << 4)) = u1;
+      }
+      if (valid && p.lse != nullptr)
+        p.lse[bh * p.S + qpos] = (mx + __log2f(l)) * 0.69314718055994530942f;
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[b]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace univl
+
+using namespace univl;
+
+// 1 if univl_fused_qkv_attention_fwd supports this shape (else the caller uses the unfused QKV GEMM + attention core)
+extern "C" int univl_fused_qkv_attention_supported(int n_seq, int heads, int S, int H) {
+  return (n_seq > 0 && heads == 12 && H == 768 && S >= 16 && S <= 128 && (S % 16) == 0) ? 1 : 0;
+}
+
+// ctx[T, H] = MHA(x[T, H]) with q/k/v = x Wqkv^T + bias computed in the same kernel (T = n_seq * S, H = heads * 64 = 768).
+// wqkv: bf16 [3H, H] (rows: query | key | value weights), bias fp32 [3H].  qkv_out (nullable): bf16 [T, 3H] copy of the
+// projected q | k | v for the backward pass.  Mask / dropout arguments as univl_attention_fwd, except the dropout
+// layout, which is row-major (see the kernel) and matched by univl_attention_bwd(..., rng_layout = 1).
+extern "C" int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const void* wqkv, long long ldw,
+                                             const float* bias, void* qkv_out, long long ld_qkv, void* o,
+                                             long long ldo, float* lse, const long long* mask_a,
+                                             const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq,
+                                             int heads, int S, int causal, float scale, float p_drop,
+                                             const unsigned long long* rng_state, unsigned long long stream_id,
+                                             void* stream) {
+  const int H = heads * 64;
+  UNIVL_CHECK_ARG(x && wqkv && bias && o, "fused_attention: null pointer");
+  UNIVL_CHECK_ARG(univl_fused_qkv_attention_supported(n_seq, heads, S, H),
+                  "fused_attention: unsupported shape n_seq=%d heads=%d S=%d (12 heads, S %% 16 == 0, 16 <= S <= 128)",
+                  n_seq, heads, S);
+  UNIVL_CHECK_ARG((ldx % 8) == 0 && (ldw % 8) == 0 && (ldo % 8) == 0 && ((uintptr_t)x & 15) == 0 &&
+                      ((uintptr_t)wqkv & 15) == 0 && ((uintptr_t)o & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+                  "fused_attention: operands must be 16-byte aligned with row strides that are multiples of 8");
+  UNIVL_CHECK_ARG(mask_a == nullptr || Wa + Fb == S, "fused_attention: mask parts (%d + %d) must cover S=%d", Wa, Fb, S);
+  UNIVL_CHECK_ARG(!(Fb > 0 && mask_a != nullptr && mask_b == nullptr), "fused_attention: missing second mask part");
+  UNIVL_CHECK_ARG(!all_pairs || Nb > 0, "fused_attention: all_pairs needs Nb > 0");
+  UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "fused_attention: bad dropout probability");
+  UNIVL_CHECK_ARG(p_drop == 0.f || rng_state != nullptr, "fused_attention: dropout needs rng_state");
+  UNIVL_CHECK_ARG(qkv_out == nullptr || ((ld_qkv % 8) == 0 && ((uintptr_t)qkv_out & 15) == 0),
+                  "fused_attention: qkv_out must be 16-byte aligned");
+  FusedAttnParams p = {};
+  p.T = n_seq * S; p.S = S; p.G = 128 / S; p.RB = p.G * S; p.n_seq = n_seq; p.heads = heads;
+  p.n_blocks = (n_seq + p.G - 1) / p.G;
+  p.bias = bias; p.o = (bf16*)o; p.ldo = ldo; p.lse = lse;
+  p.mask_a = mask_a; p.mask_b = mask_b; p.Wa = Wa; p.Fb = Fb; p.Nb = Nb > 0 ? Nb : 1; p.all_pairs = all_pairs;
+  p.causal = causal; p.scale = scale;
+  p.drop_on = p_drop > 0.f;
+  p.drop_threshold = dropout_threshold16(p_drop);
+  p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  p.rng = rng_state; p.stream = stream_id;
+  p.store_qkv = qkv_out != nullptr;
+  CUtensorMap tx, tw, tq;
+  int rc;
+  if ((rc = make_tmap(&tx, x, p.T, H, ldx, 128))) return rc;        // box {64 k, 128 rows}
+  if ((rc = make_tmap(&tw, wqkv, 3 * H, H, ldw, 64))) return rc;    // box {64 k, 64 weight rows}
+  if (qkv_out != nullptr) {
+    if ((rc = make_tmap_epi(&tq, qkv_out, false, p.T, 3 * H, ld_qkv))) return rc;  // box {64 cols, 32 rows}
+  } else {
+    tq = tx;
+  }
+  cudaError_t e = cudaFuncSetAttribute(fused_qkv_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FA_SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention smem attribute: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)p.n_blocks * heads;
+  const int grid = (int)(items < sms ? items : sms);
+  e = launch_kernel(fused_qkv_attention_fwd_kernel, dim3(grid), dim3(FA_THREADS), (size_t)FA_SMEM_BYTES,
+                    (cudaStream_t)stream, tx, tw, tq, p);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention launch: %s", cudaGetErrorString(e));
+  UNIVL_CHECK_LAUNCH("fused_qkv_attention_fwd");
+  return UNIVL_OK;
+}

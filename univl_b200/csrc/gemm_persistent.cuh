@@ -36,27 +36,6 @@ struct SmemPlan {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// bulk tensor store / reduce of one staging box; coordinates {inner (column), outer (row)}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all but the most recent N bulk groups of this thread have finished READING their shared-memory source
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 struct EpiState {
   uint8_t* stage;       // this warp's two staging buffers
   uint64_t* aux_bar;    // this warp's mbarrier for auxiliary-operand TMA loads

@@ -167,9 +167,22 @@ class UniVL(UniVLPreTrainedModel):
         return self.bert.embeddings.word_embeddings.weight.device
 
     def _encode(self, input_ids, token_type_ids, attention_mask, video_norm, video_mask):
-        """reference :299-313 (inputs already flattened / normalised)"""
+        """reference :299-313 (inputs already flattened / normalised).  The text and the visual stacks are independent
+        until the similarity / cross encoder, and at M = B*W = 1536 rows each of their kernels fills a fraction of the
+        148 SMs: the visual stack runs on a side stream forked from (and joined back into) the current one, so the two
+        stacks' sub-wave kernels share the machine — forward here, and backward too, because autograd replays every
+        node on the stream its forward ran on.  Captured as two parallel branches under CUDA-graph capture."""
+        side = rt.side_stream(self._device())
+        if side is None:
+            seq = self.bert.encode(input_ids, token_type_ids, attention_mask)
+            vis = self.visual.encode(video_norm, video_mask)
+            return seq, vis
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            vis = self.visual.encode(video_norm, video_mask)
         seq = self.bert.encode(input_ids, token_type_ids, attention_mask)
-        vis = self.visual.encode(video_norm, video_mask)
+        cur.wait_stream(side)
         return seq, vis
 
     def _cross_pairs(self, seq2d, vis2d, attention_mask, video_mask, all_pairs):

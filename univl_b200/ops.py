@@ -6,6 +6,7 @@ orchestration of a whole transformer block lives in ONE autograd.Function so a l
 saved activations are exactly the tensors listed in DESIGN.md.
 """
 import math
+import os
 
 import torch
 
@@ -176,15 +177,39 @@ def attention_fwd(q, k, v, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0):
     return o, lse
 
 
-def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0, dbias=None):
+def fused_attention_supported(n_seq, S, H):
+    """self-attention shapes the fused QKV-projection + attention kernel (csrc/fused_attn.cu) takes"""
+    if os.environ.get("UNIVL_FUSED_ATTN", "1") == "0":
+        return False
+    from . import lib
+    return bool(lib.load().univl_fused_qkv_attention_supported(int(n_seq), HEADS, int(S), int(H)))
+
+
+def fused_qkv_attention_fwd(x, wqkv, bqkv, n_seq, S, mask, p=0.0, seed=0, stream=0, save_qkv=True):
+    """ctx, lse, qkv = fused QKV projection + self-attention of x[T, H] (one tcgen05 kernel; q/k/v only reach HBM when
+    `save_qkv` — the copy the backward pass reads)."""
+    T, H = x.shape
+    _check2d(x, "fused attention x"); _check2d(wqkv, "fused attention wqkv")
+    o = _empty((T, H), BF16, x)
+    lse = _empty((n_seq * HEADS * S,), F32, x)
+    qkv = _empty((T, 3 * H), BF16, x) if save_qkv else None
+    call("univl_fused_qkv_attention_fwd", x.data_ptr(), x.stride(0), wqkv.data_ptr(), wqkv.stride(0), bqkv.data_ptr(),
+         ptr(qkv), 3 * H, o.data_ptr(), o.stride(0), lse.data_ptr(), ptr(mask.a), ptr(mask.b), mask.Wa, mask.Fb,
+         mask.Nb, int(mask.all_pairs), n_seq, HEADS, S, int(mask.causal), 1.0 / math.sqrt(64.0), float(p), seed, stream)
+    return o, lse, qkv
+
+
+def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0, dbias=None,
+                  rng_layout=0):
     """dbias: optional (dbq, dbk, dbv) fp32 [H] tensors; the kernel adds the column sums of dq / dk / dv (the projection
-    bias gradients) to them, which saves the separate column-sum pass over the [T, 3H] gradient."""
+    bias gradients) to them, which saves the separate column-sum pass over the [T, 3H] gradient.
+    rng_layout 1: the forward was the fused kernel (row-major dropout layout)."""
     dbq, dbk, dbv = dbias if dbias is not None else (None, None, None)
     call("univl_attention_bwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
          o.data_ptr(), o.stride(0), lse.data_ptr(), d_o.data_ptr(), d_o.stride(0), dq.data_ptr(), dq.stride(0),
          dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), ptr(mask.a), ptr(mask.b), mask.Wa, mask.Fb,
          mask.Nb, int(mask.all_pairs), n_seq, HEADS, Sq, Sk, int(mask.causal), 1.0 / math.sqrt(64.0), float(p), seed,
-         stream, ptr(dbq), ptr(dbk), ptr(dbv))
+         stream, int(rng_layout), ptr(dbq), ptr(dbk), ptr(dbv))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -205,15 +230,24 @@ class _Drop:
         return self.arena.next_stream()
 
 
-def attn_block_fwd(xq, xkv, n_seq, Sq, Sk, mask, w, drop):
+def attn_block_fwd(xq, xkv, n_seq, Sq, Sk, mask, w, drop, need_bwd=True):
     """LayerNorm(dropout(dense(MHA(xq, xkv))) + xq)   (reference modules/module_bert.py:220-224).
-    w: dict(q,k,v,o weights fp32 params; bq,bk,bv,bo; gamma,beta)."""
+    w: dict(q,k,v,o weights fp32 params; bq,bk,bv,bo; gamma,beta).
+    Self-attention with S % 16 == 0, S <= 128 runs the fused QKV-projection + attention kernel (the [T,3H] projections
+    reach HBM only when a backward pass will read them); other shapes use the QKV GEMM + attention-core pair."""
     arena = rt.current()
     H = xq.shape[1]
     self_attn = xkv is xq
-    sv = {"self": self_attn}
+    sv = {"self": self_attn, "fused": False}
     wqkv = arena.bf16_qkv(w["q"], w["k"], w["v"])
-    if self_attn:
+    ctx = None
+    if self_attn and fused_attention_supported(n_seq, Sq, H):
+        sa, sd = drop.stream(), drop.stream()
+        ctx, lse, qkv = fused_qkv_attention_fwd(xq, wqkv, rt.packed_bias(w["bq"], w["bk"], w["bv"]), n_seq, Sq, mask,
+                                                drop.pa, drop.seed, sa, save_qkv=need_bwd)
+        sv["qkv"] = qkv
+        sv["fused"] = True
+    elif self_attn:
         qkv = linear_fwd(xq, wqkv, rt.packed_bias(w["bq"], w["bk"], w["bv"]))
         q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
         sv["qkv"] = qkv
@@ -222,8 +256,9 @@ def attn_block_fwd(xq, xkv, n_seq, Sq, Sk, mask, w, drop):
         kv = linear_fwd(xkv, wqkv[H:], rt.packed_bias(w["bk"], w["bv"]))
         k, v = kv[:, :H], kv[:, H:]
         sv["q"], sv["kv"] = q, kv
-    sa, sd = drop.stream(), drop.stream()
-    ctx, lse = attention_fwd(q, k, v, n_seq, Sq, Sk, mask, drop.pa, drop.seed, sa)
+    if ctx is None:
+        sa, sd = drop.stream(), drop.stream()
+        ctx, lse = attention_fwd(q, k, v, n_seq, Sq, Sk, mask, drop.pa, drop.seed, sa)
     ao = linear_fwd(ctx, arena.bf16(w["o"]), w["bo"])
     y, mean, rstd = layernorm_fwd(ao, xq, w["gamma"], w["beta"], drop.ph, 1, drop.seed, sd)
     sv.update(xq=xq, xkv=xkv, ctx=ctx, lse=lse, ao=ao, mean=mean, rstd=rstd, sa=sa, sd=sd, n_seq=n_seq, Sq=Sq, Sk=Sk,
@@ -253,7 +288,8 @@ def attn_block_bwd(dy, dy2, sv, need_dxkv=True):
         dqkv = _empty((T, 3 * H), BF16, dy)
         attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctx"], sv["lse"], dctx, dqkv[:, :H],
                       dqkv[:, H:2 * H], dqkv[:, 2 * H:], sv["n_seq"], sv["Sq"], sv["Sk"], sv["mask"], sv["pa"],
-                      sv["seed"], sv["sa"], dbias=(dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]))
+                      sv["seed"], sv["sa"], dbias=(dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]),
+                      rng_layout=1 if sv["fused"] else 0)
         linear_wgrad(dqkv, sv["xq"], dwqkv)
         dxq = linear_dgrad(dqkv, sv["wqkv"], epi=EPI_ADD, aux_in=g)
         dxkv = None
@@ -322,7 +358,7 @@ class EncoderLayerFn(torch.autograd.Function):
         wa = dict(zip(ATT_KEYS, params[:10]))
         wf = dict(zip(FFN_KEYS, params[10:16]))
         drop = _Drop(p_hidden, p_attn, training)
-        y1, sva = attn_block_fwd(x, x, n_seq, S, S, mask, wa, drop)
+        y1, sva = attn_block_fwd(x, x, n_seq, S, S, mask, wa, drop, need_bwd=any(ctx.needs_input_grad))
         y2, svf = ffn_block_fwd(y1, wf, drop)
         ctx.sva, ctx.svf = sva, svf
         return y2
@@ -381,7 +417,7 @@ class DecoderLayerFn(torch.autograd.Function):
         we = dict(zip(ATT_KEYS, params[10:20]))
         wf = dict(zip(FFN_KEYS, params[20:26]))
         drop = _Drop(p_hidden, p_attn, training)
-        s, svs = attn_block_fwd(x, x, n_seq, L, L, slf_mask, ws, drop)
+        s, svs = attn_block_fwd(x, x, n_seq, L, L, slf_mask, ws, drop, need_bwd=any(ctx.needs_input_grad))
         d, sve = attn_block_fwd(s, enc, n_seq, L, Se, enc_mask, we, drop)
         y, svf = ffn_block_fwd(d, wf, drop)
         ctx.svs, ctx.sve, ctx.svf = svs, sve, svf

@@ -223,6 +223,24 @@ def current_sink():
     return sink
 
 
+_side_streams = {}
+
+
+def side_stream(device):
+    """second stream of `device` for the branch of the model that is independent of the main one (visual encoder);
+    None when disabled (UNIVL_TWO_STREAM=0).  Every fork waits for the current stream first and every join makes the
+    current stream wait for it, so tensors produced on either side are ordered for the caching allocator as well."""
+    import os
+    if os.environ.get("UNIVL_TWO_STREAM", "1") == "0" or device.type != "cuda":
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
+    s = _side_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _side_streams[key] = s
+    return s
+
+
 def packed_bias(*bs):
     """q/k/v projection biases as ONE [3H] vector for the fused QKV projection: a zero-copy view when the three
     parameters are adjacent in memory (the flat layout of univl_b200.optim.FlatParams), else a concatenated copy."""
