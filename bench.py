@@ -440,11 +440,47 @@ def main():
         v["events"].append((s, e))
         v["flops"] += 2.0 * M * N * K
         return r
+    # the fused QKV-projection + attention kernel (north_star's headline kernel) and its backward, timed the same way
+    fa = {"fwd": {"flops": 0.0, "events": []}, "bwd": {"flops": 0.0, "events": []}}
+    orig_fa_fwd, orig_fa_bwd = ops.fused_qkv_attention_fwd, ops.fused_attention_bwd
+
+    def timed_fa_fwd(x_, wqkv_, bqkv_, n_seq_, S_, *args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_fa_fwd(x_, wqkv_, bqkv_, n_seq_, S_, *args, **kw)
+        e.record()
+        T_, H_ = x_.shape
+        fa["fwd"]["events"].append((s, e))
+        fa["fwd"]["flops"] += 2.0 * T_ * 3 * H_ * H_ + 4.0 * T_ * S_ * H_       # projection + QK^T + PV
+        return r
+
+    def timed_fa_bwd(qkv_, o_, lse_, d_o_, dqkv_, n_seq_, S_, *args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_fa_bwd(qkv_, o_, lse_, d_o_, dqkv_, n_seq_, S_, *args, **kw)
+        e.record()
+        fa["bwd"]["events"].append((s, e))
+        fa["bwd"]["flops"] += 10.0 * o_.shape[0] * S_ * o_.shape[1]               # S, dP, dQ, dK, dV products
+        return r
     ops.gemm = timed_gemm
+    ops.fused_qkv_attention_fwd, ops.fused_attention_bwd = timed_fa_fwd, timed_fa_bwd
+    two_stream = os.environ.get("UNIVL_TWO_STREAM")
+    os.environ["UNIVL_TWO_STREAM"] = "0"   # per-launch durations are only meaningful when kernels do not share the GPU
     for _ in range(a.profile_steps):
         eager_step(dev_batch)
     torch.cuda.synchronize()
+    if two_stream is None:
+        del os.environ["UNIVL_TWO_STREAM"]
+    else:
+        os.environ["UNIVL_TWO_STREAM"] = two_stream
     ops.gemm = orig_gemm
+    ops.fused_qkv_attention_fwd, ops.fused_attention_bwd = orig_fa_fwd, orig_fa_bwd
+    fa_out = {}
+    for k, v in fa.items():
+        ms_k = sum(s.elapsed_time(e) for s, e in v["events"])
+        big = max((s.elapsed_time(e) for s, e in v["events"]), default=0.0)
+        fa_out[k] = {"ms_per_step": ms_k / max(1, a.profile_steps), "launches_per_step": len(v["events"]) / max(1, a.profile_steps),
+                     "tflops": v["flops"] / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0, "largest_launch_ms": big}
     per = {}
     for k, v in prof.items():
         ms_k = sum(s.elapsed_time(e) for s, e in v["events"])
@@ -461,6 +497,10 @@ def main():
             captured = json.load(f)
         traffic = captured.get("traffic_bytes_per_launch")
         pipe_util = captured.get("tensor_pipe_util_pct")  # BASELINE's second metric: ncu figures, not timed here
+        r02 = os.path.join(ROOT, "profiles", "r02_fused_attn_pipe.json")
+        if os.path.exists(r02):
+            with open(r02) as f:
+                pipe_util = json.load(f)
     except (OSError, ValueError):
         pass
 
@@ -503,6 +543,7 @@ def main():
                              "L2->SM delivery (~12 TB/s) caps them near 1.5 PFLOP/s, the same regime as the cuBLAS "
                              "peak used here"},
         "clocks": sampler.summary() if sampler else None,
+        "fused_attention": fa_out,
         "tensor_pipe_util_pct": pipe_util,
     }
     if not a.no_e2e:

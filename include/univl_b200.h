@@ -106,6 +106,14 @@ int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const void* wqkv
                                   const long long* mask_a, const long long* mask_b, int Wa, int Fb, int Nb,
                                   int all_pairs, int n_seq, int heads, int S, int causal, float scale, float p_drop,
                                   const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
+/* backward of the attention core for the same shapes, on tcgen05 (S, dP, dS, P in TMEM / shared memory only):
+ * dqkv[T,3H] = d(q | k | v) from the saved qkv, the context o, d_o and lse; dbias (nullable, fp32 [3H]) accumulates the
+ * projection-bias gradients (column sums).  Masks / dropout as the fused forward (row-major dropout layout). */
+int univl_fused_attention_bwd(const void* qkv, long long ld_qkv, const void* o, long long ldo, const float* lse,
+                              const void* d_o, long long lddo, void* dqkv, long long ld_dqkv, float* dbias,
+                              const long long* mask_a, const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs,
+                              int n_seq, int heads, int S, int causal, float scale, float p_drop,
+                              const unsigned long long* rng_state, unsigned long long stream_id, void* stream);
 
 /* ---- utilities ------------------------------------------------------------------------------------------------ */
 int univl_colsum_bf16(const void* x, long long ld, float* out, int rows, int cols, void* stream); /* bias grads */

@@ -284,6 +284,55 @@ def test_fused_qkv_attention_fwd_matches_unfused_and_fp32(n_seq, S, causal):
     assert none is None and torch.equal(o3, o)
 
 
+@pytest.mark.parametrize("n_seq,S,causal,p", [(3, 48, False, 0.0), (2, 96, False, 0.0), (2, 128, True, 0.0),
+                                              (5, 32, False, 0.0), (9, 16, True, 0.0), (1, 112, False, 0.0),
+                                              (40, 96, False, 0.0), (3, 48, False, 0.25), (2, 128, False, 0.25),
+                                              (301, 48, False, 0.1)])
+def test_fused_attention_bwd_matches_fp32_and_unfused_backward(n_seq, S, causal, p):
+    """tcgen05 attention backward: (p = 0) against fp32 autograd of the same op, and (any p) against the mma.sync
+    backward kernel regenerating the same row-major dropout mask; bias-gradient column sums included."""
+    H, h = 768, 12
+    x, w, b, mask = _fused_inputs(n_seq, S, 100 + S + n_seq)
+    spec = ops.MaskSpec(mask, causal=causal)
+    o, lse, qkv = ops.fused_qkv_attention_fwd(x, w, b, n_seq, S, spec, p=p, seed=RNG.data_ptr(), stream=7)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    d_o = _bf(torch.randn(n_seq * S, H, device=DEV, generator=g))
+    dqkv = torch.empty_like(qkv)
+    dbias = torch.ones(3 * H, device=DEV)
+    ops.fused_attention_bwd(qkv, o, lse, d_o, dqkv, n_seq, S, spec, p=p, seed=RNG.data_ptr(), stream=7, dbias=dbias)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    # (a) the mma.sync backward on the same saved tensors and the same dropout layout
+    dq2 = torch.empty_like(qkv)
+    db2 = torch.ones(3, H, device=DEV)
+    ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, lse, d_o, dq2[:, :H], dq2[:, H:2 * H],
+                      dq2[:, 2 * H:], n_seq, S, S, spec, p=p, seed=RNG.data_ptr(), stream=7,
+                      dbias=(db2[0], db2[1], db2[2]), rng_layout=1)
+    scale = max(1.0, float(dq2.float().abs().max()))
+    assert (dqkv.float() - dq2.float()).abs().max() <= 3e-2 * scale
+    rel = float((dqkv.float() - dq2.float()).norm() / dq2.float().norm())
+    assert rel <= 1e-2, rel
+    tol = dqkv.float().abs().sum(0) * 2.0 ** -7 + 2e-3
+    assert bool(((dbias - 1.0 - dqkv.float().sum(0)).abs() <= tol).all())
+    if p == 0.0:
+        # (b) fp32 autograd
+        def heads(t):
+            return t.float().view(n_seq, S, h, 64).permute(0, 2, 1, 3)
+        qf = heads(qkv[:, :H]).requires_grad_()
+        kf = heads(qkv[:, H:2 * H]).requires_grad_()
+        vf = heads(qkv[:, 2 * H:]).requires_grad_()
+        add = (1.0 - mask.float()).view(n_seq, 1, 1, S) * -10000.0
+        if causal:
+            fut = torch.triu(torch.ones(S, S, device=DEV), diagonal=1).view(1, 1, S, S)
+            add = ((1.0 - mask.float()).view(n_seq, 1, 1, S) + fut).gt(0).float() * -10000.0
+        ref = _attn_ref(qf, kf, vf, add).permute(0, 2, 1, 3).reshape(n_seq * S, H)
+        ref.backward(d_o.float())
+        for n, gr in enumerate((qf.grad, kf.grad, vf.grad)):
+            want = gr.permute(0, 2, 1, 3).reshape(n_seq * S, H)
+            got = dqkv[:, n * H:(n + 1) * H].float()
+            assert (got - want).abs().max() <= 4e-2 * max(1.0, float(want.abs().max())), n
+
+
 def test_fused_qkv_attention_all_pairs_masks():
     Na, Nb, W, F, H = 3, 4, 16, 32, 768
     S = W + F

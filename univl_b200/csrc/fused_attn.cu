@@ -368,17 +368,21 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       uint8_t* prow = smem + FA_OFF_P + row * 128;
       const int sw = row & 7;
       float mx = -INFINITY, l = 0.f;
-      if (valid) {
-        for (int c = 0; c < p.S; c += 16) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(t_s + c0 + c, r);
-          tmem_ld_wait();
+      // tcgen05.ld is warp-collective (.sync.aligned, one column address for the whole warp), and with packed sequences
+      // (S < 64) the lanes of a warp can belong to different sequences: every lane walks ALL key chunks and only does
+      // arithmetic on the chunks of its own sequence.
+      for (int c = 0; c < NK; c += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_s + c, r);
+        tmem_ld_wait();
+        if (valid && c >= c0 && c < c0 + p.S) {
+          const int kc = c - c0;
           float t[16];
           float cm = -INFINITY;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float a = madd[c0 + c + e];
-            if (p.causal && (c + e) > qpos && a == 0.f) a = neg_big;
+            float a = madd[c + e];
+            if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
             t[e] = fmaf(__uint_as_float(r[e]), sl2, a);
             cm = fmaxf(cm, t[e]);
           }
@@ -395,10 +399,10 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       // P row: zeros outside the own sequence (block-diagonal) and for rows that carry no query
       for (int c = 0; c < NK; c += 16) {
         uint4 u0 = make_uint4(0, 0, 0, 0), u1 = make_uint4(0, 0, 0, 0);
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_s + c, r);  // warp-uniform (see above)
+        tmem_ld_wait();
         if (valid && c >= c0 && c < c0 + p.S) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(t_s + c, r);
-          tmem_ld_wait();
           const int kc = c - c0;  // key position inside the sequence (multiple of 16)
           float pr[16];
 #pragma unroll
@@ -512,5 +516,392 @@ extern "C" int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const
                     (cudaStream_t)stream, tx, tw, tq, p);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention launch: %s", cudaGetErrorString(e));
   UNIVL_CHECK_LAUNCH("fused_qkv_attention_fwd");
+  return UNIVL_OK;
+}
+
+// =====================================================================================================================
+// Backward of the attention core on tcgen05 (same row-block x head decomposition, same masks and dropout layout as the
+// forward above).  Inputs: the saved q | k | v [T, 3H], the context O and its gradient dO [T, H], the log-sum-exp.
+// Per item, five small tensor-core products with every intermediate on chip:
+//     S  = Q K^T,  dP = dO V^T                         (TMEM, fp32)
+//     P  = exp(S * scale + mask - lse);  P~ = dropout(P);  dS = P o (dropout'(dP) - D) * scale,  D_i = sum_d dO_id O_id
+//          one thread per (query row, half of the key chunks): tcgen05.ld, Philox, bf16 P~ and dS tiles -> shared memory
+//     dQ = dS K   (A = dS K-major,  B = K MN-major)    dV = P~^T dO (A = P~ MN-major, B = dO MN-major)
+//     dK = dS^T Q (A = dS MN-major, B = Q MN-major)    -> TMEM -> bf16 rows of dq | dk | dv [T, 3H]
+// and the projection-bias gradients (column sums of dQ / dK / dV) by a shuffle transpose-reduction + red.global.add.
+// The Q, K, V, dO operand tiles arrive by TMA straight in the 128B-swizzled layout every product reads (the "major" of an
+// operand is a descriptor bit), double-buffered so the loads of item j+1 overlap the math of item j.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 compute (two per TMEM lane quarter,
+// alternating 16-key chunks in the softmax-backward phase and splitting the 192 gradient columns in the drain phase).
+// =====================================================================================================================
+namespace univl {
+
+constexpr int FB_IN_BYTES = 4 * FA_TILE_BYTES;              // Q, K, V, dO tiles of one item
+constexpr int FB_OFF_P = 2 * FB_IN_BYTES;                   // P~ tile (two 64-key atoms)
+constexpr int FB_OFF_DS = FB_OFF_P + 2 * FA_TILE_BYTES;     // dS tile
+constexpr int FB_OFF_MADD = FB_OFF_DS + 2 * FA_TILE_BYTES;
+constexpr int FB_OFF_BAR = FB_OFF_MADD + 512;
+constexpr int FB_NUM_BARS = 8;                              // in_full[2] in_empty[2] sd_full pds_ready acc_full acc_free
+constexpr int FB_SMEM_BYTES = FB_OFF_BAR + FB_NUM_BARS * 8 + 16 + 1024;
+constexpr int FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DQ = 256, FB_COL_DK = 320, FB_COL_DV = 384;
+
+struct FusedAttnBwdParams {
+  int T, S, G, RB, n_seq, heads, n_blocks;
+  const bf16* o;
+  long long ldo;
+  const bf16* d_o;
+  long long lddo;
+  const float* lse;
+  bf16* dqkv;
+  long long ld_dqkv;
+  float* dbias;               // [3 * heads * 64] accumulated into, or null
+  const long long* mask_a;
+  const long long* mask_b;
+  int Wa, Fb, Nb, all_pairs, causal;
+  float scale;
+  int drop_on;
+  uint32_t drop_threshold;
+  float drop_scale;
+  const unsigned long long* rng;
+  uint64_t stream;
+};
+
+// column totals of a 32-lane x 32-column block held one row per lane: after the call lane l holds the sum over the 32
+// lanes of v[l].  Halving butterfly: 16 + 8 + 4 + 2 + 1 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      // keep the columns whose bit `half` equals this lane's; send the other half to the partner lane
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                           const FusedAttnBwdParams p_in) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + FB_OFF_BAR);   // [2] TMA -> MMA
+  uint64_t* in_empty = in_full + 2;                                      // [2] MMA commit -> TMA
+  uint64_t* sd_full = in_empty + 2;                                      // S, dP complete        (MMA commit -> compute)
+  uint64_t* pds_ready = sd_full + 1;                                     // P~, dS tiles written; S / dP read (compute -> MMA)
+  uint64_t* acc_full = pds_ready + 1;                                    // dQ, dK, dV complete   (MMA commit -> compute)
+  uint64_t* acc_free = acc_full + 1;                                     // dQ, dK, dV drained    (compute -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+  float* madd = reinterpret_cast<float*>(smem + FB_OFF_MADD);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  FusedAttnBwdParams p = p_in;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&in_full[b], 1);
+      mbar_init(&in_empty[b], 1);
+    }
+    mbar_init(sd_full, 1);
+    mbar_init(pds_ready, 8);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  int item_begin, item_end;
+  fa_item_range(p.n_blocks * p.heads, item_begin, item_end);
+  const int n_items = item_end - item_begin;
+  const int NK = p.RB;
+  const int H = p.heads * 64;
+
+  if (warp == 0) {
+    // ------------------------------------------ TMA producer ------------------------------------------
+    if (lane == 0) {
+      for (int j = 0; j < n_items; ++j) {
+        const int b = j & 1;
+        const int w = item_begin + j;
+        const int rb = w / p.heads, h = w - rb * p.heads;
+        const int r0 = rb * p.RB;
+        mbar_wait(&in_empty[b], (((uint32_t)j >> 1) & 1) ^ 1);
+        uint8_t* dst = smem + b * FB_IN_BYTES;
+        mbar_arrive_expect_tx(&in_full[b], FB_IN_BYTES);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) tma_load_2d(dst + m * FA_TILE_BYTES, &tmap_qkv, &in_full[b], m * H + h * 64, r0);
+        tma_load_2d(dst + 3 * FA_TILE_BYTES, &tmap_do, &in_full[b], h * 64, r0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------ MMA issuer --------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, NK, false, false);
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
+      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
+      const uint32_t sP = smem_u32(smem + FB_OFF_P), sdS = smem_u32(smem + FB_OFF_DS);
+      for (int j = 0; j < n_items; ++j) {
+        const int b = j & 1;
+        const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES), sK = sQ + FA_TILE_BYTES, sV = sK + FA_TILE_BYTES,
+                       sdO = sV + FA_TILE_BYTES;
+        mbar_wait(&in_full[b], ((uint32_t)j >> 1) & 1);
+        tc_fence_after_sync();
+        // S / dP columns are free: pds_ready of item j-1 was waited for below, in the previous iteration
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + FB_COL_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                    make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + FB_COL_DP, make_smem_desc_sw128(sdO + k * 32, 16, 1024),
+                    make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sd_full);
+        mbar_wait(pds_ready, (uint32_t)j & 1);
+        mbar_wait(acc_free, ((uint32_t)j & 1) ^ 1);  // gradients of item j-1 drained out of TMEM
+        tc_fence_after_sync();
+        for (int kk = 0; kk < NK / 16; ++kk)  // dQ[q, d] = sum_key dS[q, key] K[key, d]
+          umma_bf16(tmem_base + FB_COL_DQ, make_smem_desc_sw128(sdS + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(sK + kk * 2048, FA_TILE_BYTES, 1024), idesc_dq, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) {      // contraction over the 128 query rows of the tile (rows >= RB hold zeros)
+          umma_bf16(tmem_base + FB_COL_DV, make_smem_desc_sw128(sP + kk * 2048, FA_TILE_BYTES, 1024),
+                    make_smem_desc_sw128(sdO + kk * 2048, FA_TILE_BYTES, 1024), idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + FB_COL_DK, make_smem_desc_sw128(sdS + kk * 2048, FA_TILE_BYTES, 1024),
+                    make_smem_desc_sw128(sQ + kk * 2048, FA_TILE_BYTES, 1024), idesc_t, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(acc_full);
+        umma_commit(&in_empty[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------ compute warps -----------------------------------------
+    const uint64_t seed = (p.drop_on && p.rng != nullptr) ? p.rng[0] : 0ull;
+    const uint64_t stream = p.stream + ((p.drop_on && p.rng != nullptr) ? (p.rng[1] << 20) : 0ull);
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;       // which warp of the lane quarter's pair
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int g = row / p.S;
+    const int c0 = g * p.S;
+    const int qpos = row - c0;
+    const float sl2 = p.scale * 1.44269504088896340736f;
+    const float neg_big = -10000.0f * 1.44269504088896340736f;
+    int cur_rb = -1;
+    for (int j = 0; j < n_items; ++j) {
+      const int w = item_begin + j;
+      const int rb = w / p.heads, h = w - rb * p.heads;
+      if (rb != cur_rb) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+          float m = 0.f;
+          if (row < NK) {
+            const long long seq = (long long)rb * p.G + g;
+            long long mv = 1;
+            if (p.mask_a != nullptr && seq < p.n_seq) {
+              const long long mi = p.all_pairs ? seq / p.Nb : seq, mj = p.all_pairs ? seq % p.Nb : seq;
+              if (qpos < p.Wa) mv = p.mask_a[mi * p.Wa + qpos];
+              else if (p.mask_b != nullptr) mv = p.mask_b[mj * p.Fb + (qpos - p.Wa)];
+            }
+            m = mv != 0 ? 0.f : neg_big;
+          }
+          madd[row] = m;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_rb = rb;
+      }
+      const long long seq = (long long)rb * p.G + g;
+      const long long tok = (long long)rb * p.RB + row;
+      const bool valid = row < p.RB && seq < p.n_seq;
+      const long long bh = seq * p.heads + h;
+      // D_i = <dO_i, O_i> over the 64 dims of this head, and the row's log-sum-exp (log2 domain)
+      float D = 0.f, lse2 = 0.f;
+      if (valid) {
+        const uint4* po = reinterpret_cast<const uint4*>(p.o + tok * p.ldo + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + tok * p.lddo + h * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 uo = __ldg(po + c), ud = __ldg(pd + c);
+          const uint32_t wo[4] = {uo.x, uo.y, uo.z, uo.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack_bf16x2(wo[e]), bb = unpack_bf16x2(wd[e]);
+            D = fmaf(a.x, bb.x, D);
+            D = fmaf(a.y, bb.y, D);
+          }
+        }
+        lse2 = p.lse[bh * p.S + qpos] * 1.44269504088896340736f;
+      }
+      mbar_wait(sd_full, (uint32_t)j & 1);
+      tc_fence_after_sync();
+      uint8_t* prow = smem + FB_OFF_P + row * 128;
+      uint8_t* srow = smem + FB_OFF_DS + row * 128;
+      const int sw = row & 7;
+      const float ds_scale = p.drop_on ? p.drop_scale : 1.0f;
+      for (int c = half * 16; c < NK; c += 32) {   // this warp's 16-key chunks
+        uint4 pu0 = make_uint4(0, 0, 0, 0), pu1 = pu0, su0 = pu0, su1 = pu0;
+        uint32_t rs[16], rp[16];
+        // warp-collective loads (one column address per warp); lanes of other packed sequences ignore the chunk
+        tmem_ld_32x32b_x16(tmem_base + FB_COL_S + lane_base + c, rs);
+        tmem_ld_32x32b_x16(tmem_base + FB_COL_DP + lane_base + c, rp);
+        tmem_ld_wait();
+        if (valid && c >= c0 && c < c0 + p.S) {
+          const int kc = c - c0;
+          uint32_t keep = 0xFFFFu;
+          if (p.drop_on) {
+            const uint64_t base = ((uint64_t)bh * p.S + qpos) * (uint64_t)(p.S >> 3) + (uint64_t)(kc >> 3);
+            keep = 0;
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              const uint4 rnd = philox4x32(seed, stream, base + g8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (philox_u16(rnd, e) < p.drop_threshold) keep |= 1u << (g8 * 8 + e);
+            }
+          }
+          float pd[16], dsv[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a = madd[c + e];
+            if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
+            const float pr = ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, a) - lse2);
+            const bool kp = (keep >> e) & 1u;
+            const float gdrop = kp ? __uint_as_float(rp[e]) * ds_scale : 0.f;
+            pd[e] = kp ? pr * ds_scale : 0.f;
+            dsv[e] = pr * (gdrop - D) * p.scale;
+          }
+          pu0.x = pack_bf16x2(pd[0], pd[1]);   pu0.y = pack_bf16x2(pd[2], pd[3]);
+          pu0.z = pack_bf16x2(pd[4], pd[5]);   pu0.w = pack_bf16x2(pd[6], pd[7]);
+          pu1.x = pack_bf16x2(pd[8], pd[9]);   pu1.y = pack_bf16x2(pd[10], pd[11]);
+          pu1.z = pack_bf16x2(pd[12], pd[13]); pu1.w = pack_bf16x2(pd[14], pd[15]);
+          su0.x = pack_bf16x2(dsv[0], dsv[1]);   su0.y = pack_bf16x2(dsv[2], dsv[3]);
+          su0.z = pack_bf16x2(dsv[4], dsv[5]);   su0.w = pack_bf16x2(dsv[6], dsv[7]);
+          su1.x = pack_bf16x2(dsv[8], dsv[9]);   su1.y = pack_bf16x2(dsv[10], dsv[11]);
+          su1.z = pack_bf16x2(dsv[12], dsv[13]); su1.w = pack_bf16x2(dsv[14], dsv[15]);
+        }
+        const int atom = c >> 6, chunk = (c & 63) >> 3;
+        const int o0 = atom * FA_TILE_BYTES + ((chunk ^ sw) << 4), o1 = atom * FA_TILE_BYTES + (((chunk + 1) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(prow + o0) = pu0;
+        *reinterpret_cast<uint4*>(prow + o1) = pu1;
+        *reinterpret_cast<uint4*>(srow + o0) = su0;
+        *reinterpret_cast<uint4*>(srow + o1) = su1;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+
+      // ---- drain: rows = tile rows (queries for dQ, keys for dK / dV); this warp's 96 of the 192 gradient columns ----
+      mbar_wait(acc_full, (uint32_t)j & 1);
+      tc_fence_after_sync();
+      const bool row_ok = row < p.RB && tok < p.T;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        // warp half 0: dQ[0:32) dQ[32:64) dK[0:32) ; half 1: dK[32:64) dV[0:32) dV[32:64)
+        const int idx = half * 3 + part;             // 32-column block index 0..5 over dQ | dK | dV
+        const int m = idx >> 1, cb = (idx & 1) * 32;
+        const uint32_t tcol = (m == 0 ? FB_COL_DQ : m == 1 ? FB_COL_DK : FB_COL_DV) + cb;
+        uint32_t r0[16], r1[16];
+        tmem_ld_32x32b_x16(tmem_base + tcol + lane_base, r0);
+        tmem_ld_32x32b_x16(tmem_base + tcol + 16 + lane_base, r1);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          v[e] = row_ok ? __uint_as_float(r0[e]) : 0.f;
+          v[16 + e] = row_ok ? __uint_as_float(r1[e]) : 0.f;
+        }
+        if (row_ok) {
+          bf16* dst = p.dqkv + tok * p.ld_dqkv + m * H + h * 64 + cb;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint4 u;
+            u.x = pack_bf16x2(v[c8 * 8 + 0], v[c8 * 8 + 1]);
+            u.y = pack_bf16x2(v[c8 * 8 + 2], v[c8 * 8 + 3]);
+            u.z = pack_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5]);
+            u.w = pack_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + c8 * 8) = u;
+          }
+        }
+        if (p.dbias != nullptr) {
+          const float tot = warp_colsum32(v, lane);  // lane l: column cb + l summed over this warp's 32 rows
+          if (tot != 0.f) atomicAdd(p.dbias + m * H + h * 64 + cb + lane, tot);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace univl
+
+// dq | dk | dv [T, 3H] (bf16) = backward of the attention core for the shapes univl_fused_qkv_attention_supported
+// accepts, from the saved q | k | v [T, 3H], the context o, its gradient d_o and the log-sum-exp.  dbias (nullable, fp32
+// [3H]) accumulates the column sums (projection-bias gradients).  Dropout masks: the row-major layout of the fused forward.
+extern "C" int univl_fused_attention_bwd(const void* qkv, long long ld_qkv, const void* o, long long ldo,
+                                         const float* lse, const void* d_o, long long lddo, void* dqkv,
+                                         long long ld_dqkv, float* dbias, const long long* mask_a,
+                                         const long long* mask_b, int Wa, int Fb, int Nb, int all_pairs, int n_seq,
+                                         int heads, int S, int causal, float scale, float p_drop,
+                                         const unsigned long long* rng_state, unsigned long long stream_id,
+                                         void* stream) {
+  const int H = heads * 64;
+  UNIVL_CHECK_ARG(qkv && o && lse && d_o && dqkv, "fused_attention_bwd: null pointer");
+  UNIVL_CHECK_ARG(univl_fused_qkv_attention_supported(n_seq, heads, S, H),
+                  "fused_attention_bwd: unsupported shape n_seq=%d heads=%d S=%d", n_seq, heads, S);
+  UNIVL_CHECK_ARG((ld_qkv % 8) == 0 && (ldo % 8) == 0 && (lddo % 8) == 0 && (ld_dqkv % 8) == 0 &&
+                      ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)o & 15) == 0 && ((uintptr_t)d_o & 15) == 0 &&
+                      ((uintptr_t)dqkv & 15) == 0,
+                  "fused_attention_bwd: operands must be 16-byte aligned with row strides that are multiples of 8");
+  UNIVL_CHECK_ARG(mask_a == nullptr || Wa + Fb == S, "fused_attention_bwd: mask parts must cover S");
+  UNIVL_CHECK_ARG(!(Fb > 0 && mask_a != nullptr && mask_b == nullptr), "fused_attention_bwd: missing second mask part");
+  UNIVL_CHECK_ARG(!all_pairs || Nb > 0, "fused_attention_bwd: all_pairs needs Nb > 0");
+  UNIVL_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng_state != nullptr),
+                  "fused_attention_bwd: bad dropout arguments");
+  FusedAttnBwdParams p = {};
+  p.T = n_seq * S; p.S = S; p.G = 128 / S; p.RB = p.G * S; p.n_seq = n_seq; p.heads = heads;
+  p.n_blocks = (n_seq + p.G - 1) / p.G;
+  p.o = (const bf16*)o; p.ldo = ldo; p.d_o = (const bf16*)d_o; p.lddo = lddo; p.lse = lse;
+  p.dqkv = (bf16*)dqkv; p.ld_dqkv = ld_dqkv; p.dbias = dbias;
+  p.mask_a = mask_a; p.mask_b = mask_b; p.Wa = Wa; p.Fb = Fb; p.Nb = Nb > 0 ? Nb : 1; p.all_pairs = all_pairs;
+  p.causal = causal; p.scale = scale;
+  p.drop_on = p_drop > 0.f;
+  p.drop_threshold = dropout_threshold16(p_drop);
+  p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  p.rng = rng_state; p.stream = stream_id;
+  CUtensorMap tq, td;
+  int rc;
+  if ((rc = make_tmap(&tq, qkv, p.T, 3 * H, ld_qkv, 128))) return rc;   // box {64 cols, 128 rows}
+  if ((rc = make_tmap(&td, d_o, p.T, H, lddo, 128))) return rc;
+  cudaError_t e = cudaFuncSetAttribute(fused_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FB_SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention_bwd smem attribute: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)p.n_blocks * heads;
+  const int grid = (int)(items < sms ? items : sms);
+  e = launch_kernel(fused_attention_bwd_kernel, dim3(grid), dim3(FA_THREADS), (size_t)FB_SMEM_BYTES,
+                    (cudaStream_t)stream, tq, td, p);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention_bwd launch: %s", cudaGetErrorString(e));
+  UNIVL_CHECK_LAUNCH("fused_attention_bwd");
   return UNIVL_OK;
 }

@@ -199,6 +199,15 @@ def fused_qkv_attention_fwd(x, wqkv, bqkv, n_seq, S, mask, p=0.0, seed=0, stream
     return o, lse, qkv
 
 
+def fused_attention_bwd(qkv, o, lse, d_o, dqkv, n_seq, S, mask, p=0.0, seed=0, stream=0, dbias=None):
+    """dqkv[T, 3H] = backward of the attention core on tcgen05 (csrc/fused_attn.cu) for the shapes the fused forward
+    takes; dbias: optional contiguous fp32 [3H] the column sums are added to."""
+    call("univl_fused_attention_bwd", qkv.data_ptr(), qkv.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
+         d_o.data_ptr(), d_o.stride(0), dqkv.data_ptr(), dqkv.stride(0), ptr(dbias), ptr(mask.a), ptr(mask.b), mask.Wa,
+         mask.Fb, mask.Nb, int(mask.all_pairs), n_seq, HEADS, S, int(mask.causal), 1.0 / math.sqrt(64.0), float(p), seed,
+         stream)
+
+
 def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, n_seq, Sq, Sk, mask, p=0.0, seed=0, stream=0, dbias=None,
                   rng_layout=0):
     """dbias: optional (dbq, dbk, dbv) fp32 [H] tensors; the kernel adds the column sums of dq / dk / dv (the projection
@@ -286,10 +295,14 @@ def attn_block_bwd(dy, dy2, sv, need_dxkv=True):
     if sv["self"]:
         qkv = sv["qkv"]
         dqkv = _empty((T, 3 * H), BF16, dy)
-        attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctx"], sv["lse"], dctx, dqkv[:, :H],
-                      dqkv[:, H:2 * H], dqkv[:, 2 * H:], sv["n_seq"], sv["Sq"], sv["Sk"], sv["mask"], sv["pa"],
-                      sv["seed"], sv["sa"], dbias=(dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]),
-                      rng_layout=1 if sv["fused"] else 0)
+        if sv["fused"] and os.environ.get("UNIVL_FUSED_ATTN_BWD", "1") != "0":
+            fused_attention_bwd(qkv, sv["ctx"], sv["lse"], dctx, dqkv, sv["n_seq"], sv["Sq"], sv["mask"], sv["pa"],
+                                sv["seed"], sv["sa"], dbias=dbqkv)
+        else:
+            attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctx"], sv["lse"], dctx, dqkv[:, :H],
+                          dqkv[:, H:2 * H], dqkv[:, 2 * H:], sv["n_seq"], sv["Sq"], sv["Sk"], sv["mask"], sv["pa"],
+                          sv["seed"], sv["sa"], dbias=(dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]),
+                          rng_layout=1 if sv["fused"] else 0)
         linear_wgrad(dqkv, sv["xq"], dwqkv)
         dxq = linear_dgrad(dqkv, sv["wqkv"], epi=EPI_ADD, aux_in=g)
         dxkv = None
