@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
     ap.add_argument("--profile_steps", type=int, default=2)
+    ap.add_argument("--grad_payload", default="bf16", choices=["bf16", "f32"],
+                    help="N > 1: dtype of the gradient all-reduce payload (bf16 halves the NVLink bytes)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (falls back to eager "
                     "launches if capture fails), 0: eager")
     return ap.parse_args()
@@ -290,7 +292,7 @@ def main():
     opt = FusedBertAdam(groups, lr=lr, warmup=0.1, t_total=100000, max_grad_norm=1.0, global_clip_norm=1.0,
                         grad_scale=1.0 / world, model=model)
     opt._build()
-    reducer = FlatGradReducer(opt.p, opt.g, n_buckets=4)
+    reducer = FlatGradReducer(opt.p, opt.g, n_buckets=4, compress="bf16" if a.grad_payload == "bf16" else None)
 
     host_batch = synth.make_batch(cfg, seed=1234 + rank, b=a.batch)
     host_batch = {k: v.pin_memory() for k, v in host_batch.items()}
@@ -349,9 +351,11 @@ def main():
                     static_loss = eager_step(static_batch)
                 else:
                     static_loss = fwd_bwd(static_batch)
+                    reducer.pack()          # fp32 gradients -> bf16 payload, inside the backward graph
             if world > 1:
                 graph_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph_opt):
+                    reducer.unpack()        # summed payload -> fp32 gradient buffer
                     opt.step()
             launches_per_step = rt.launch_count() - n0
             torch.cuda.synchronize()
@@ -363,7 +367,7 @@ def main():
                         static_batch[k].copy_(v, non_blocking=True)
                 graph.replay()
                 if graph_opt is not None:
-                    reducer.all_reduce()
+                    reducer.all_reduce(packed=True)
                     graph_opt.replay()
                 return static_loss
             for _ in range(2):
@@ -521,6 +525,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": samples, "parallelism": "dp%d" % world,
                    "dropout": a.dropout, "optimizer": "fused BertAdam + clip (in timed region)",
+                   "grad_allreduce": ("NCCL sum, %s payload, after backward" % a.grad_payload) if world > 1 else "none",
                    "launch": "cuda-graph replay" if graphed else "eager",
                    "l2": "per-step working set (~6 GB of activations at FT-Align b=32) exceeds the 126 MB L2"},
         "gpu_launches": launches, "loss": loss_val,

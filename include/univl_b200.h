@@ -118,6 +118,7 @@ int univl_fused_attention_bwd(const void* qkv, long long ld_qkv, const void* o, 
 /* ---- utilities ------------------------------------------------------------------------------------------------ */
 int univl_colsum_bf16(const void* x, long long ld, float* out, int rows, int cols, void* stream); /* bias grads */
 int univl_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+int univl_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream); /* bf16 gradient payload -> fp32 */
 int univl_multi_cast_f32_to_bf16(const unsigned long long* device_table, int n_tensors, int blocks_per_tensor,
                                  void* stream);
 int univl_fill_f32(float* p, float value, long long n, void* stream);

@@ -36,6 +36,17 @@ def _worker(rank, world, port, out):
         want = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
         ok &= bool(torch.equal(g, want))
         ok &= abs(red.grad_scale - 1.0 / world) < 1e-12
+        # bf16 payload: same sums up to bf16 rounding of the addends and of the result (2^-8 relative in total)
+        g2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        red2 = FlatGradReducer(p, g2, n_buckets=2, broadcast=False, compress="bf16")
+        red2.all_reduce()
+        ok &= bool(((g2 - want).abs() <= 2.0 ** -7 * want.abs() + 1e-6).all()) and red2.payload.dtype == torch.bfloat16
+        g3 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        red3 = FlatGradReducer(p, g3, n_buckets=2, broadcast=False, compress="bf16")
+        red3.pack()                                        # the split form bench.py captures into its two graphs
+        red3.all_reduce(packed=True)
+        red3.unpack()
+        ok &= bool(torch.equal(g3, g2))
         out[rank] = ok
     finally:
         dist.destroy_process_group()

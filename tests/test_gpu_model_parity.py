@@ -9,6 +9,14 @@ Stated tolerances (bf16 activations, fp32 accumulation / statistics / losses; th
          cross-entropy losses over the vocabulary / frames (caption, pretrain-II):            |d| <= 2e-3 * |loss|
          MIL-NCE on UN-normalised dot products (use_mil): |d| <= 2^-8 * max|sim| — the logits are only resolved to
          bf16 precision relative to their magnitude (~25 here)
+         pretrain stage-two (five objectives summed): 2e-3 * |loss| for the three vocabulary / similarity cross-entropies
+         + 2^-7 * (max|joint sim| + MFM-NCE loss value) for the two NCE terms whose logits are UN-normalised dot products of
+         two bf16-rounded vectors (each operand carries 2^-9 relative error, 2^-8 on the product; the NCE loss inherits the
+         absolute error of its largest logits, and a loss of L nats means logits of magnitude >= L).  With the stress
+         weights these logits reach 40-65; with the reference's init law the same case agrees to 1e-2.
+  similarity matrix   mean-pool (cosine) similarity: |d| <= 2^-7.  Cross-encoder similarity (FT-Align: similarity_dense of
+         the pooled cross output): |d| <= 2^-5 * max(1, max|sim|) — a 768-term dot product of hidden values that carry
+         the stack's ~1e-2 relative error with a weight vector of norm 0.55 (init law) / 1.1 (stress weights).
   hidden states   relative Frobenius error <= 2 * sqrt(7 * (layers + 1)) * 2^-9 / sqrt(3).  Derivation: every layer
                   stores 7 bf16 tensors on the path to its output (qkv, context, attention-out, LN1-out, FFN
                   pre-activation / activation, FFN-out, LN2-out; +1 "layer" for the embedding / input projection); a
@@ -58,13 +66,16 @@ def _record(name, **kw):
         pass
 
 
-def loss_tolerance(cfg, gold):
+def loss_tolerance(cfg, gold, parts=None):
     init_law = bool(gold.get("weight_kwargs", {}).get("init_law"))
     if cfg.mode in ("ft_joint", "ft_align"):
         return 1e-3 if (init_law or cfg.mode == "ft_joint") else 4e-3
     if cfg.use_mil and not getattr(cfg, "stage_two", False):
         return 2.0 ** -8 * max(float(s.abs().max()) for s in gold["sim_matrices"])
-    return 2e-3 * abs(gold["loss"])
+    tol = 2e-3 * abs(gold["loss"])
+    if cfg.mode == "pretrain2" and parts is not None:
+        tol += 2.0 ** -7 * (float(gold["sim_matrices"][0].abs().max()) + float(parts["mfm_loss"]))
+    return tol
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -79,7 +90,10 @@ def test_loss_hidden_and_grads_match_reference(name):
     loss.backward()
     torch.cuda.synchronize()
     got = float(loss.detach())
-    tol = loss_tolerance(cfg, gold)
+    o_loss = parts = o_grads = None
+    if name not in GOLDEN_ONLY:
+        o_loss, parts, o_grads = run_oracle(cfg, batch, sd=sd, backward=True)
+    tol = loss_tolerance(cfg, gold, parts)
     _record(name, loss=got, ref_loss=gold["loss"], loss_err=abs(got - gold["loss"]), loss_tol=tol)
     assert abs(got - gold["loss"]) <= tol, "loss %r vs reference %r (tol %g)" % (got, gold["loss"], tol)
     grads = grads_by_name(model)
@@ -97,7 +111,8 @@ def test_loss_hidden_and_grads_match_reference(name):
             ref_sim = gold["sim_matrices"][-1]
             sim_err = float((sim - ref_sim).abs().max())
             _record(name, sim_max_err=sim_err, sim_scale=float(ref_sim.abs().max()))
-            assert sim_err <= 2.0 ** -7 * max(1.0, float(ref_sim.abs().max())), sim_err
+            sim_tol = 2.0 ** -7 if cfg.mode == "ft_joint" else 2.0 ** -5 * max(1.0, float(ref_sim.abs().max()))
+            assert sim_err <= sim_tol, (sim_err, sim_tol)
     seq, vis = seq.float().cpu(), vis.float().cpu()
     assert (seq[:, :6, :16] - gold["seq_slice"]).abs().max() <= 1e-1
     assert (vis[:, :6, :16] - gold["vis_slice"]).abs().max() <= 1e-1
@@ -118,7 +133,6 @@ def test_loss_hidden_and_grads_match_reference(name):
         assert worst <= 0.06, worst
         return
 
-    o_loss, parts, o_grads = run_oracle(cfg, batch, sd=sd, backward=True)
     assert abs(got - float(o_loss)) <= tol
     # hidden states after an L-layer bf16 stack against the fp32 reference algorithm: derived bound on the relative
     # Frobenius error (see the module docstring); worst single element ~6 bf16 ulps of |x| = 2..4.

@@ -217,6 +217,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// non-suspending probe (mbarrier.try_wait may put the thread to sleep for a system-dependent time when the phase is not
+// complete: fine for a blocking wait, wrong for a scheduler that polls several barriers)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a pipeline bug must surface as a trap (launch failure), never as
 // a hung GPU.  try_wait already suspends in hardware, so the spin count stays low
 // in healthy runs; 1<<26 polls is many seconds.

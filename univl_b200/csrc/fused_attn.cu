@@ -24,14 +24,15 @@
 // thread interleaves the short S / PV products of item j between projection k-blocks of item j+1 as soon as their
 // operands are ready (mbarrier polling), so the tensor pipe only idles when it is genuinely starved.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain (TMEM lane quarter = warp & 3),
-// warps 6-9 softmax.  All synchronisation is mbarrier-based (tcgen05.commit on the MMA side).
+// Warp roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain (TMEM lane quarter = warp & 3),
+// warps 6-13 softmax (two per quarter, alternating 16-key chunks).  All synchronisation is mbarrier-based (tcgen05.commit on the MMA side).
 #include "common.cuh"
 #include "tmap.cuh"
 
 namespace univl {
 
-constexpr int FA_THREADS = 320;
+constexpr int FA_THREADS = 448;   // forward: TMA + MMA + 4 drain + 8 softmax warps
+constexpr int FB_THREADS = 320;   // backward: TMA + MMA + 8 compute warps
 constexpr int FA_STAGES = 3;
 constexpr int FA_KB = 12;                       // 768 / 64 k-blocks
 constexpr int FA_X_BYTES = 128 * 64 * 2;        // 16 KB: x rows of one k-block
@@ -43,7 +44,8 @@ constexpr int FA_OFF_K = FA_OFF_Q + FA_TILE_BYTES;
 constexpr int FA_OFF_V = FA_OFF_K + FA_TILE_BYTES;
 constexpr int FA_OFF_P = FA_OFF_V + FA_TILE_BYTES;            // two 64-key atoms
 constexpr int FA_OFF_MADD = FA_OFF_P + 2 * FA_TILE_BYTES;     // 128 floats
-constexpr int FA_OFF_BAR = FA_OFF_MADD + 512;
+constexpr int FA_OFF_XCH = FA_OFF_MADD + 512;                 // softmax pair exchange: max[2][128], sum[2][128] floats
+constexpr int FA_OFF_BAR = FA_OFF_XCH + 2048;
 // full[3] empty[3] acc_full[2] s_full[2] p_ready[2] pv_done[2] half_free[2] qkv_ready[1]
 constexpr int FA_NUM_BARS = 2 * FA_STAGES + 11;
 constexpr int FA_SMEM_BYTES = FA_OFF_BAR + FA_NUM_BARS * 8 + 16 + 1024;
@@ -69,7 +71,7 @@ struct FusedAttnParams {
 };
 
 __device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity, bool blocking) {
-  if (!blocking) return mbar_try_wait(bar, parity) != 0;
+  if (!blocking) return mbar_test_wait(bar, parity) != 0;
   mbar_wait(bar, parity);
   return true;
 }
@@ -114,7 +116,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_ready[b], 4);    // one arrival per softmax warp
+      mbar_init(&p_ready[b], 8);    // one arrival per softmax warp
       mbar_init(&pv_done[b], 1);
       mbar_init(&half_free[b], 4);  // one arrival per drain warp
     }
@@ -191,9 +193,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       };
       auto wait_serving = [&](uint64_t* bar, uint32_t parity) {
         uint32_t spins = 0;
-        while (!mbar_try_wait(bar, parity)) {
+        while (!mbar_test_wait(bar, parity)) {
           try_core(false);
-          if (++spins > (1u << 24)) {
+          if (++spins > (1u << 26)) {
             printf("univl: fused attention MMA wait timed out (block %d)\n", blockIdx.x);
             __trap();
           }
@@ -324,12 +326,13 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     if (p.store_qkv && lane == 0) bulk_wait_read<0>();
   } else {
     // ------------------------------------------ softmax warps -----------------------------------------
-    if (p.drop_on && p.rng != nullptr) {
-      // device-side {seed, epoch}: fresh masks on every CUDA-graph replay (see common.cuh / univl_rng_advance)
-    }
-    const uint64_t seed = (p.drop_on && p.rng != nullptr) ? p.rng[0] : 0ull;
+    // Two warps per TMEM lane quarter; a thread owns one query row and every other 16-key chunk (chunk parity = which
+    // warp of the pair), holds its <= 64 logits in registers (one TMEM read, one exp per element), and the pair combines
+    // row max / row sum through shared memory between two named barriers.
+    const uint64_t seed = (p.drop_on && p.rng != nullptr) ? p.rng[0] : 0ull;   // device-side {seed, epoch}
     const uint64_t stream = p.stream + ((p.drop_on && p.rng != nullptr) ? (p.rng[1] << 20) : 0ull);
     const int q = warp & 3;
+    const int half = (warp - 6) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int g = row / p.S;                 // packed sequence this query row belongs to
@@ -337,6 +340,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     const int qpos = row - c0;
     const float sl2 = p.scale * 1.44269504088896340736f;
     const float neg_big = -10000.0f * 1.44269504088896340736f;
+    float* xmax = reinterpret_cast<float*>(smem + FA_OFF_XCH);   // [2][128]
+    float* xsum = xmax + 256;                                    // [2][128]
+    const int pair_bar = 2 + q;
     int cur_rb = -1;
     for (int j = 0; j < n_items; ++j) {
       const int b = j & 1;
@@ -344,20 +350,22 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       const int rb = w / p.heads, h = w - rb * p.heads;
       if (rb != cur_rb) {
         // additive key mask of this row block (log2 domain): 0 / -10000 per key column; shared by the 12 heads
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // every softmax warp is done with the previous block's mask
-        float m = 0.f;
-        if (row < NK) {
-          const long long seq = (long long)rb * p.G + g;
-          long long mv = 1;
-          if (p.mask_a != nullptr && seq < p.n_seq) {
-            const long long mi = p.all_pairs ? seq / p.Nb : seq, mj = p.all_pairs ? seq % p.Nb : seq;
-            if (qpos < p.Wa) mv = p.mask_a[mi * p.Wa + qpos];
-            else if (p.mask_b != nullptr) mv = p.mask_b[mj * p.Fb + (qpos - p.Wa)];
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // every softmax warp is done with the previous block's mask
+        if (half == 0) {
+          float m = 0.f;
+          if (row < NK) {
+            const long long seq = (long long)rb * p.G + g;
+            long long mv = 1;
+            if (p.mask_a != nullptr && seq < p.n_seq) {
+              const long long mi = p.all_pairs ? seq / p.Nb : seq, mj = p.all_pairs ? seq % p.Nb : seq;
+              if (qpos < p.Wa) mv = p.mask_a[mi * p.Wa + qpos];
+              else if (p.mask_b != nullptr) mv = p.mask_b[mj * p.Fb + (qpos - p.Wa)];
+            }
+            m = mv != 0 ? 0.f : neg_big;
           }
-          m = mv != 0 ? 0.f : neg_big;
+          madd[row] = m;
         }
-        madd[row] = m;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_rb = rb;
       }
       mbar_wait(&s_full[b], ((uint32_t)j >> 1) & 1);
@@ -367,72 +375,83 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       const uint32_t t_s = tmem_base + b * FA_HALF_COLS + lane_base;
       uint8_t* prow = smem + FA_OFF_P + row * 128;
       const int sw = row & 7;
-      float mx = -INFINITY, l = 0.f;
-      // tcgen05.ld is warp-collective (.sync.aligned, one column address for the whole warp), and with packed sequences
-      // (S < 64) the lanes of a warp can belong to different sequences: every lane walks ALL key chunks and only does
-      // arithmetic on the chunks of its own sequence.
-      for (int c = 0; c < NK; c += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_s + c, r);
-        tmem_ld_wait();
-        if (valid && c >= c0 && c < c0 + p.S) {
+      // logits of this thread's chunks (tcgen05.ld is warp-collective: every lane loads every chunk of the warp's parity;
+      // with packed sequences only the chunks of the lane's own sequence are used)
+      float t[4][16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = half * 16 + i * 32;
+        if (c < NK) {   // warp-uniform
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_s + c, r);
+          tmem_ld_wait();
+          const bool own = valid && c >= c0 && c < c0 + p.S;
           const int kc = c - c0;
-          float t[16];
-          float cm = -INFINITY;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float a = madd[c + e];
             if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
-            t[e] = fmaf(__uint_as_float(r[e]), sl2, a);
-            cm = fmaxf(cm, t[e]);
+            t[i][e] = own ? fmaf(__uint_as_float(r[e]), sl2, a) : -INFINITY;
+            mx = fmaxf(mx, t[i][e]);
           }
-          const float nm = fmaxf(mx, cm);
-          float acc = 0.f;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) acc += ex2_approx(t[e] - nm);
-          l = l * ex2_approx(mx - nm) + acc;
-          mx = nm;
         }
       }
+      xmax[half * 128 + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(xmax[row], xmax[128 + row]);
+      const float mref = valid ? mx : 0.f;   // rows without a query: keep the arithmetic finite
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = half * 16 + i * 32;
+        if (c < NK) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            t[i][e] = ex2_approx(t[i][e] - mref);   // exp2(-inf) = 0 outside the own sequence
+            l += t[i][e];
+          }
+        }
+      }
+      xsum[half * 128 + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l = xsum[row] + xsum[128 + row];
       const float inv = valid ? (p.drop_on ? p.drop_scale : 1.0f) / l : 0.f;
       const long long bh = seq * p.heads + h;
-      // P row: zeros outside the own sequence (block-diagonal) and for rows that carry no query
-      for (int c = 0; c < NK; c += 16) {
-        uint4 u0 = make_uint4(0, 0, 0, 0), u1 = make_uint4(0, 0, 0, 0);
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_s + c, r);  // warp-uniform (see above)
-        tmem_ld_wait();
-        if (valid && c >= c0 && c < c0 + p.S) {
-          const int kc = c - c0;  // key position inside the sequence (multiple of 16)
-          float pr[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float a = madd[c + e];
-            if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
-            pr[e] = ex2_approx(fmaf(__uint_as_float(r[e]), sl2, a) - mx) * inv;
-          }
-          if (p.drop_on) {
-            // row-major dropout layout: element (bh, query, key) = 16-bit word (key & 7) of
-            // Philox(seed, stream, (bh * S + query) * (S / 8) + key / 8)
-            const uint64_t base = ((uint64_t)bh * p.S + qpos) * (uint64_t)(p.S >> 3) + (uint64_t)(kc >> 3);
+      for (int i = 0; i < 4; ++i) {
+        const int c = half * 16 + i * 32;
+        if (c < NK) {
+          const bool own = valid && c >= c0 && c < c0 + p.S;
+          uint4 u0 = make_uint4(0, 0, 0, 0), u1 = make_uint4(0, 0, 0, 0);
+          if (own) {   // zeros outside the own sequence (block-diagonal) and for rows that carry no query
+            float pr[16];
 #pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
-              const uint4 rnd = philox4x32(seed, stream, base + g8);
+            for (int e = 0; e < 16; ++e) pr[e] = t[i][e] * inv;
+            if (p.drop_on) {
+              // row-major dropout layout: element (bh, query, key) = 16-bit word (key & 7) of
+              // Philox(seed, stream, (bh * S + query) * (S / 8) + key / 8)
+              const int kc = c - c0;
+              const uint64_t base = ((uint64_t)bh * p.S + qpos) * (uint64_t)(p.S >> 3) + (uint64_t)(kc >> 3);
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (philox_u16(rnd, e) >= p.drop_threshold) pr[g8 * 8 + e] = 0.f;
+              for (int g8 = 0; g8 < 2; ++g8) {
+                const uint4 rnd = philox4x32(seed, stream, base + g8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (philox_u16(rnd, e) >= p.drop_threshold) pr[g8 * 8 + e] = 0.f;
+              }
             }
+            u0.x = pack_bf16x2(pr[0], pr[1]);   u0.y = pack_bf16x2(pr[2], pr[3]);
+            u0.z = pack_bf16x2(pr[4], pr[5]);   u0.w = pack_bf16x2(pr[6], pr[7]);
+            u1.x = pack_bf16x2(pr[8], pr[9]);   u1.y = pack_bf16x2(pr[10], pr[11]);
+            u1.z = pack_bf16x2(pr[12], pr[13]); u1.w = pack_bf16x2(pr[14], pr[15]);
           }
-          u0.x = pack_bf16x2(pr[0], pr[1]);   u0.y = pack_bf16x2(pr[2], pr[3]);
-          u0.z = pack_bf16x2(pr[4], pr[5]);   u0.w = pack_bf16x2(pr[6], pr[7]);
-          u1.x = pack_bf16x2(pr[8], pr[9]);   u1.y = pack_bf16x2(pr[10], pr[11]);
-          u1.z = pack_bf16x2(pr[12], pr[13]); u1.w = pack_bf16x2(pr[14], pr[15]);
+          const int atom = c >> 6, chunk = (c & 63) >> 3;
+          *reinterpret_cast<uint4*>(prow + atom * FA_TILE_BYTES + ((chunk ^ sw) << 4)) = u0;
+          *reinterpret_cast<uint4*>(prow + atom * FA_TILE_BYTES + (((chunk + 1) ^ sw) << 4)) = u1;
         }
-        const int atom = c >> 6, chunk = (c & 63) >> 3;
-        *reinterpret_cast<uint4*>(prow + atom * FA_TILE_BYTES + ((chunk ^ sw) << 4)) = u0;
-        *reinterpret_cast<uint4*>(prow + atom * FA_TILE_BYTES + (((chunk + 1) ^ sw) << 4)) = u1;
       }
-      if (valid && p.lse != nullptr)
+      if (half == 0 && valid && p.lse != nullptr)
         p.lse[bh * p.S + qpos] = (mx + __log2f(l)) * 0.69314718055994530942f;
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -529,21 +548,25 @@ extern "C" int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const
 //     dQ = dS K   (A = dS K-major,  B = K MN-major)    dV = P~^T dO (A = P~ MN-major, B = dO MN-major)
 //     dK = dS^T Q (A = dS MN-major, B = Q MN-major)    -> TMEM -> bf16 rows of dq | dk | dv [T, 3H]
 // and the projection-bias gradients (column sums of dQ / dK / dV) by a shuffle transpose-reduction + red.global.add.
-// The Q, K, V, dO operand tiles arrive by TMA straight in the 128B-swizzled layout every product reads (the "major" of an
-// operand is a descriptor bit), double-buffered so the loads of item j+1 overlap the math of item j.
+// The Q, K, V, dO (and O, for D) tiles arrive by TMA straight in the 128B-swizzled layout every product reads (the "major"
+// of an operand is a descriptor bit), double-buffered; TMEM is split in two buffers so S / dP of item j+1 are computed
+// while the compute warps are still busy with item j.
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 compute (two per TMEM lane quarter,
 // alternating 16-key chunks in the softmax-backward phase and splitting the 192 gradient columns in the drain phase).
 // =====================================================================================================================
 namespace univl {
 
-constexpr int FB_IN_BYTES = 4 * FA_TILE_BYTES;              // Q, K, V, dO tiles of one item
+constexpr int FB_IN_BYTES = 5 * FA_TILE_BYTES;              // Q, K, V, dO, O tiles of one item
 constexpr int FB_OFF_P = 2 * FB_IN_BYTES;                   // P~ tile (two 64-key atoms)
 constexpr int FB_OFF_DS = FB_OFF_P + 2 * FA_TILE_BYTES;     // dS tile
 constexpr int FB_OFF_MADD = FB_OFF_DS + 2 * FA_TILE_BYTES;
 constexpr int FB_OFF_BAR = FB_OFF_MADD + 512;
-constexpr int FB_NUM_BARS = 8;                              // in_full[2] in_empty[2] sd_full pds_ready acc_full acc_free
+constexpr int FB_NUM_BARS = 11;                             // in_full[2] in_empty[2] sd_full[2] pds_ready acc_full[2] acc_free[2]
 constexpr int FB_SMEM_BYTES = FB_OFF_BAR + FB_NUM_BARS * 8 + 16 + 1024;
-constexpr int FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DQ = 256, FB_COL_DK = 320, FB_COL_DV = 384;
+// TMEM: two 256-column buffers alternate between consecutive items.  Inside a buffer S and dP come first; once the compute
+// warps have consumed them the same columns receive dQ | dK | dV.
+constexpr int FB_BUF_COLS = 256;
+constexpr int FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DQ = 0, FB_COL_DK = 64, FB_COL_DV = 128;
 
 struct FusedAttnBwdParams {
   int T, S, G, RB, n_seq, heads, n_blocks;
@@ -583,19 +606,19 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FB_THREADS, 1)
 fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                           const FusedAttnBwdParams p_in) {
+                           const __grid_constant__ CUtensorMap tmap_o, const FusedAttnBwdParams p_in) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + FB_OFF_BAR);   // [2] TMA -> MMA
   uint64_t* in_empty = in_full + 2;                                      // [2] MMA commit -> TMA
-  uint64_t* sd_full = in_empty + 2;                                      // S, dP complete        (MMA commit -> compute)
-  uint64_t* pds_ready = sd_full + 1;                                     // P~, dS tiles written; S / dP read (compute -> MMA)
-  uint64_t* acc_full = pds_ready + 1;                                    // dQ, dK, dV complete   (MMA commit -> compute)
-  uint64_t* acc_free = acc_full + 1;                                     // dQ, dK, dV drained    (compute -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+  uint64_t* sd_full = in_empty + 2;                                      // [2] S, dP complete      (MMA commit -> compute)
+  uint64_t* pds_ready = sd_full + 2;                                     // P~, dS tiles written; S / dP read (compute -> MMA)
+  uint64_t* acc_full = pds_ready + 1;                                    // [2] dQ, dK, dV complete (MMA commit -> compute)
+  uint64_t* acc_free = acc_full + 2;                                     // [2] dQ, dK, dV drained  (compute -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
   float* madd = reinterpret_cast<float*>(smem + FB_OFF_MADD);
 
   const int warp = threadIdx.x >> 5;
@@ -605,14 +628,15 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_o);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&in_full[b], 1);
       mbar_init(&in_empty[b], 1);
+      mbar_init(&sd_full[b], 1);
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_free[b], 8);
     }
-    mbar_init(sd_full, 1);
     mbar_init(pds_ready, 8);
-    mbar_init(acc_full, 1);
-    mbar_init(acc_free, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -642,6 +666,7 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
 #pragma unroll
         for (int m = 0; m < 3; ++m) tma_load_2d(dst + m * FA_TILE_BYTES, &tmap_qkv, &in_full[b], m * H + h * 64, r0);
         tma_load_2d(dst + 3 * FA_TILE_BYTES, &tmap_do, &in_full[b], h * 64, r0);
+        tma_load_2d(dst + 4 * FA_TILE_BYTES, &tmap_o, &in_full[b], h * 64, r0);
       }
     }
   } else if (warp == 1) {
@@ -651,35 +676,43 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
       constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
       const uint32_t sP = smem_u32(smem + FB_OFF_P), sdS = smem_u32(smem + FB_OFF_DS);
-      for (int j = 0; j < n_items; ++j) {
+      // S = Q K^T and dP = dO V^T of item j into TMEM buffer j & 1 (free once the gradients of item j-2 are drained)
+      auto issue_sdp = [&](int j) {
         const int b = j & 1;
         const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES), sK = sQ + FA_TILE_BYTES, sV = sK + FA_TILE_BYTES,
                        sdO = sV + FA_TILE_BYTES;
+        const uint32_t tb = tmem_base + b * FB_BUF_COLS;
         mbar_wait(&in_full[b], ((uint32_t)j >> 1) & 1);
+        mbar_wait(&acc_free[b], (((uint32_t)j >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        // S / dP columns are free: pds_ready of item j-1 was waited for below, in the previous iteration
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + FB_COL_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+          umma_bf16(tb + FB_COL_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
                     make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + FB_COL_DP, make_smem_desc_sw128(sdO + k * 32, 16, 1024),
+          umma_bf16(tb + FB_COL_DP, make_smem_desc_sw128(sdO + k * 32, 16, 1024),
                     make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sd_full);
+        umma_commit(&sd_full[b]);
+      };
+      if (n_items > 0) issue_sdp(0);
+      for (int j = 0; j < n_items; ++j) {
+        const int b = j & 1;
+        const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES), sK = sQ + FA_TILE_BYTES, sdO = sK + 2 * FA_TILE_BYTES;
+        const uint32_t tb = tmem_base + b * FB_BUF_COLS;
+        if (j + 1 < n_items) issue_sdp(j + 1);   // runs while the compute warps work on item j
         mbar_wait(pds_ready, (uint32_t)j & 1);
-        mbar_wait(acc_free, ((uint32_t)j & 1) ^ 1);  // gradients of item j-1 drained out of TMEM
         tc_fence_after_sync();
         for (int kk = 0; kk < NK / 16; ++kk)  // dQ[q, d] = sum_key dS[q, key] K[key, d]
-          umma_bf16(tmem_base + FB_COL_DQ, make_smem_desc_sw128(sdS + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+          umma_bf16(tb + FB_COL_DQ, make_smem_desc_sw128(sdS + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(sK + kk * 2048, FA_TILE_BYTES, 1024), idesc_dq, kk > 0 ? 1u : 0u);
         for (int kk = 0; kk < 8; ++kk) {      // contraction over the 128 query rows of the tile (rows >= RB hold zeros)
-          umma_bf16(tmem_base + FB_COL_DV, make_smem_desc_sw128(sP + kk * 2048, FA_TILE_BYTES, 1024),
+          umma_bf16(tb + FB_COL_DV, make_smem_desc_sw128(sP + kk * 2048, FA_TILE_BYTES, 1024),
                     make_smem_desc_sw128(sdO + kk * 2048, FA_TILE_BYTES, 1024), idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(tmem_base + FB_COL_DK, make_smem_desc_sw128(sdS + kk * 2048, FA_TILE_BYTES, 1024),
+          umma_bf16(tb + FB_COL_DK, make_smem_desc_sw128(sdS + kk * 2048, FA_TILE_BYTES, 1024),
                     make_smem_desc_sw128(sQ + kk * 2048, FA_TILE_BYTES, 1024), idesc_t, kk > 0 ? 1u : 0u);
         }
-        umma_commit(acc_full);
+        umma_commit(&acc_full[b]);
         umma_commit(&in_empty[b]);
       }
     }
@@ -723,14 +756,21 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       const long long tok = (long long)rb * p.RB + row;
       const bool valid = row < p.RB && seq < p.n_seq;
       const long long bh = seq * p.heads + h;
-      // D_i = <dO_i, O_i> over the 64 dims of this head, and the row's log-sum-exp (log2 domain)
-      float D = 0.f, lse2 = 0.f;
-      if (valid) {
-        const uint4* po = reinterpret_cast<const uint4*>(p.o + tok * p.ldo + h * 64);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + tok * p.lddo + h * 64);
+      const int b = j & 1;
+      const uint32_t tb = tmem_base + b * FB_BUF_COLS;
+      const float lse2 = valid ? p.lse[bh * p.S + qpos] * 1.44269504088896340736f : 0.f;
+      mbar_wait(&in_full[b], ((uint32_t)j >> 1) & 1);   // the item's operand tiles (dO, O read below) have landed
+      mbar_wait(&sd_full[b], ((uint32_t)j >> 1) & 1);   // S, dP in TMEM
+      tc_fence_after_sync();
+      // D_i = <dO_i, O_i> over the 64 dims of this head, from the swizzled dO / O tiles in shared memory
+      float D = 0.f;
+      {
+        const uint8_t* drow = smem + b * FB_IN_BYTES + 3 * FA_TILE_BYTES + row * 128;
+        const uint8_t* orow = drow + FA_TILE_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const uint4 uo = __ldg(po + c), ud = __ldg(pd + c);
+          const int off = (c ^ (row & 7)) << 4;
+          const uint4 ud = *reinterpret_cast<const uint4*>(drow + off), uo = *reinterpret_cast<const uint4*>(orow + off);
           const uint32_t wo[4] = {uo.x, uo.y, uo.z, uo.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -739,10 +779,7 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
             D = fmaf(a.y, bb.y, D);
           }
         }
-        lse2 = p.lse[bh * p.S + qpos] * 1.44269504088896340736f;
       }
-      mbar_wait(sd_full, (uint32_t)j & 1);
-      tc_fence_after_sync();
       uint8_t* prow = smem + FB_OFF_P + row * 128;
       uint8_t* srow = smem + FB_OFF_DS + row * 128;
       const int sw = row & 7;
@@ -801,7 +838,7 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       if (lane == 0) mbar_arrive(pds_ready);
 
       // ---- drain: rows = tile rows (queries for dQ, keys for dK / dV); this warp's 96 of the 192 gradient columns ----
-      mbar_wait(acc_full, (uint32_t)j & 1);
+      mbar_wait(&acc_full[b], ((uint32_t)j >> 1) & 1);
       tc_fence_after_sync();
       const bool row_ok = row < p.RB && tok < p.T;
 #pragma unroll
@@ -811,8 +848,8 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
         const int m = idx >> 1, cb = (idx & 1) * 32;
         const uint32_t tcol = (m == 0 ? FB_COL_DQ : m == 1 ? FB_COL_DK : FB_COL_DV) + cb;
         uint32_t r0[16], r1[16];
-        tmem_ld_32x32b_x16(tmem_base + tcol + lane_base, r0);
-        tmem_ld_32x32b_x16(tmem_base + tcol + 16 + lane_base, r1);
+        tmem_ld_32x32b_x16(tb + tcol + lane_base, r0);
+        tmem_ld_32x32b_x16(tb + tcol + 16 + lane_base, r1);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -839,7 +876,7 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_free);
+      if (lane == 0) mbar_arrive(&acc_free[b]);
     }
   }
 
@@ -887,10 +924,11 @@ extern "C" int univl_fused_attention_bwd(const void* qkv, long long ld_qkv, cons
   p.drop_threshold = dropout_threshold16(p_drop);
   p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   p.rng = rng_state; p.stream = stream_id;
-  CUtensorMap tq, td;
+  CUtensorMap tq, td, to;
   int rc;
   if ((rc = make_tmap(&tq, qkv, p.T, 3 * H, ld_qkv, 128))) return rc;   // box {64 cols, 128 rows}
   if ((rc = make_tmap(&td, d_o, p.T, H, lddo, 128))) return rc;
+  if ((rc = make_tmap(&to, o, p.T, H, ldo, 128))) return rc;
   cudaError_t e = cudaFuncSetAttribute(fused_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        FB_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention_bwd smem attribute: %s", cudaGetErrorString(e));
@@ -899,8 +937,8 @@ extern "C" int univl_fused_attention_bwd(const void* qkv, long long ld_qkv, cons
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long items = (long long)p.n_blocks * heads;
   const int grid = (int)(items < sms ? items : sms);
-  e = launch_kernel(fused_attention_bwd_kernel, dim3(grid), dim3(FA_THREADS), (size_t)FB_SMEM_BYTES,
-                    (cudaStream_t)stream, tq, td, p);
+  e = launch_kernel(fused_attention_bwd_kernel, dim3(grid), dim3(FB_THREADS), (size_t)FB_SMEM_BYTES,
+                    (cudaStream_t)stream, tq, td, to, p);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention_bwd launch: %s", cudaGetErrorString(e));
   UNIVL_CHECK_LAUNCH("fused_attention_bwd");
   return UNIVL_OK;

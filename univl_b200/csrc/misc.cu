@@ -168,6 +168,32 @@ extern "C" int univl_cast_f32_to_bf16(const float* src, void* dst, long long n, 
   return UNIVL_OK;
 }
 
+namespace univl {
+// dst(fp32) = src(bf16): the gradient payload coming back from a bf16 all-reduce (univl_b200/ddp.py)
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + i * 8);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    *reinterpret_cast<float4*>(dst + i * 8) = make_float4(a.x, a.y, b.x, b.y);
+    *reinterpret_cast<float4*>(dst + i * 8 + 4) = make_float4(c.x, c.y, d.x, d.y);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) dst[i] = __bfloat162float(src[i]);
+}
+}  // namespace univl
+
+extern "C" int univl_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
+  UNIVL_CHECK_ARG(src && dst && n >= 0, "cast: bad arguments");
+  UNIVL_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "cast_bf16_to_f32: 16-byte alignment");
+  if (n == 0) return UNIVL_OK;
+  long long blocks = (n + 2047) / 2048;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_bf16_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  UNIVL_CHECK_LAUNCH("cast_bf16_to_f32");
+  return UNIVL_OK;
+}
+
 // device table of n_tensors x {src, dst, count} (uint64 each); one launch refreshes every bf16 weight copy
 extern "C" int univl_multi_cast_f32_to_bf16(const unsigned long long* device_table, int n_tensors, int blocks_per_tensor,
                                             void* stream) {
