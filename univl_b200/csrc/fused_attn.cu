@@ -26,6 +26,8 @@
 //
 // Warp roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain (TMEM lane quarter = warp & 3),
 // warps 6-13 softmax (two per quarter, alternating 16-key chunks).  All synchronisation is mbarrier-based (tcgen05.commit on the MMA side).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tmap.cuh"
 
@@ -68,6 +70,7 @@ struct FusedAttnParams {
   const unsigned long long* rng;
   uint64_t stream;
   int store_qkv;
+  int item_order;
 };
 
 __device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity, bool blocking) {
@@ -84,6 +87,45 @@ __device__ __forceinline__ void fa_item_range(int total, int& begin, int& end) {
   end = begin + per + (b < rem ? 1 : 0);
 }
 
+// Item j of this CTA -> (row block, head).  order 0: a contiguous range of (block, head) items, heads fastest.  order 1
+// ("synchronised heads"): CTA c owns row blocks c, c + grid, c + 2 grid, ... and walks the 12 heads of each, so at any
+// moment all CTAs stream the SAME head's weight slices (requests for one L2 line arrive together) while each re-reads
+// only its own activation rows.
+struct FaItems {
+  int order, begin, count, heads, unit, n_units;
+  // unit / n_units: index and number of the workers that walk items (CTAs, or 2-CTA clusters whose "row block" is a pair)
+  __device__ __forceinline__ void init(int order_, int n_blocks, int heads_, int unit_, int n_units_) {
+    order = order_; heads = heads_; unit = unit_; n_units = n_units_;
+    if (order == 0) {
+      const int total = n_blocks * heads;
+      const int per = total / n_units, rem = total % n_units;
+      begin = unit * per + min(unit, rem);
+      count = per + (unit < rem ? 1 : 0);
+    } else {
+      begin = 0;
+      const int mine = (unit < n_blocks) ? (n_blocks - 1 - unit) / n_units + 1 : 0;
+      count = mine * heads;
+    }
+  }
+  __device__ __forceinline__ void decode(int j, int& rb, int& h) const {
+    if (order == 0) {
+      const int w = begin + j;
+      rb = w / heads;
+      h = w - rb * heads;
+    } else {
+      const int r = j / heads;
+      h = j - r * heads;
+      rb = unit + r * n_units;
+    }
+  }
+};
+
+// MC = true: launched as clusters of two CTAs that walk the same (row-block pair, head) items, CTA r on row block
+// 2 * pair + r.  Both need the same 24 KB weight slice per k-block: each CTA issues HALF of its TMA boxes with
+// .multicast::cluster, so the slice leaves L2 once per pair (the kernel is bound by L2 -> SM operand delivery: 491 KB per
+// item without sharing, 343 KB with it).  A stage slot is free when BOTH CTAs' MMAs have consumed it (the peer writes
+// into it too): tcgen05.commit multicasts the "slot free" arrival to both CTAs' barriers.
+template <bool MC>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                                const __grid_constant__ CUtensorMap tmap_qkv, const FusedAttnParams p_in) {
@@ -111,7 +153,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     if (p.store_qkv) tma_prefetch_desc(&tmap_qkv);
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);   // MC: this CTA's and the peer's MMA both release the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -125,14 +167,17 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
-  __syncthreads();
+  if (MC) cluster_barrier();   // barrier inits of both CTAs visible cluster-wide before any remote TMA / commit signal
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  int item_begin, item_end;
-  fa_item_range(p.n_blocks * p.heads, item_begin, item_end);
-  const int n_items = item_end - item_begin;
+  const int crank = MC ? (int)cluster_rank() : 0;
+  FaItems items;
+  if (MC) items.init(p.item_order, (p.n_blocks + 1) >> 1, p.heads, (int)blockIdx.x >> 1, (int)gridDim.x >> 1);
+  else items.init(p.item_order, p.n_blocks, p.heads, (int)blockIdx.x, (int)gridDim.x);
+  const int n_items = items.count;
   const int NK = p.RB;  // keys per block (S % 16 == 0, so RB is a multiple of 16)
 
   if (warp == 0) {
@@ -140,8 +185,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     if (lane == 0) {
       uint32_t it = 0;
       for (int j = 0; j < n_items; ++j) {
-        const int w = item_begin + j;
-        const int rb = w / p.heads, h = w - rb * p.heads;
+        int rb, h;
+        items.decode(j, rb, h);
+        if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
         const int r0 = rb * p.RB;
         for (int kb = 0; kb < FA_KB; ++kb, ++it) {
           const int s = it % FA_STAGES;
@@ -151,9 +197,19 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
           uint8_t* sw = sx + FA_X_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], FA_STAGE_BYTES);
           tma_load_2d(sx, &tmap_x, &full_bar[s], kb * 64, r0);  // rows >= T arrive as zeros
+          if (!MC) {
 #pragma unroll
-          for (int m = 0; m < 3; ++m)  // q / k / v weight rows of head h: rows m*H + h*64 of Wqkv[3H, 768]
-            tma_load_2d(sw + m * 8192, &tmap_w, &full_bar[s], kb * 64, m * p.heads * 64 + h * 64);
+            for (int m = 0; m < 3; ++m)  // q / k / v weight rows of head h: rows m*H + h*64 of Wqkv[3H, 768]
+              tma_load_2d(sw + m * 8192, &tmap_w, &full_bar[s], kb * 64, m * p.heads * 64 + h * 64);
+          } else {
+            // six 32-row boxes (q lo/hi, k lo/hi, v lo/hi); this CTA issues three of them, to both CTAs
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int bx = 3 * crank + i;
+              tma_load_2d_mc(sw + bx * 4096, &tmap_w, &full_bar[s], kb * 64,
+                             (bx >> 1) * p.heads * 64 + h * 64 + (bx & 1) * 32, (uint16_t)3);
+            }
+          }
         }
       }
     }
@@ -219,7 +275,8 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
           for (int k = 0; k < 4; ++k)
             umma_bf16(d_tmem, make_smem_desc_sw128(sx + k * 32, 16, 1024), make_smem_desc_sw128(sw + k * 32, 16, 1024),
                       idesc_proj, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          if (MC) umma_commit_mc(&empty_bar[s], (uint16_t)3);
+          else umma_commit(&empty_bar[s]);
         }
         umma_commit(&acc_full[b]);
       }
@@ -234,8 +291,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       if (jj >= 1) {
         // ---- O of item jj-1 -> merged-head context rows ----
         const int j = jj - 1, b = j & 1;
-        const int w = item_begin + j;
-        const int rb = w / p.heads, h = w - rb * p.heads;
+        int rb, h;
+        items.decode(j, rb, h);
+        if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
         mbar_wait(&pv_done[b], ((uint32_t)j >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t t_o = tmem_base + b * FA_HALF_COLS + FA_O_COL + lane_base;
@@ -268,8 +326,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       if (jj < n_items) {
         // ---- projection accumulators of item jj -> Q / K / V operand tiles (Q/K/V/P of item jj-1 are free: pv_done) ----
         const int j = jj, b = j & 1;
-        const int w = item_begin + j;
-        const int rb = w / p.heads, h = w - rb * p.heads;
+        int rb, h;
+        items.decode(j, rb, h);
+        if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
         mbar_wait(&acc_full[b], ((uint32_t)j >> 1) & 1);
         tc_fence_after_sync();
         if (p.store_qkv && jj >= 1) {
@@ -346,8 +405,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     int cur_rb = -1;
     for (int j = 0; j < n_items; ++j) {
       const int b = j & 1;
-      const int w = item_begin + j;
-      const int rb = w / p.heads, h = w - rb * p.heads;
+      int rb, h;
+      items.decode(j, rb, h);
+      if (MC) rb = 2 * rb + crank;
       if (rb != cur_rb) {
         // additive key mask of this row block (log2 domain): 0 / -10000 per key column; shared by the 12 heads
         asm volatile("bar.sync 1, 256;" ::: "memory");  // every softmax warp is done with the previous block's mask
@@ -461,7 +521,8 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (MC) cluster_barrier();   // the peer may still multicast into this CTA's shared memory / signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -514,25 +575,41 @@ extern "C" int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const
   p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   p.rng = rng_state; p.stream = stream_id;
   p.store_qkv = qkv_out != nullptr;
+  {
+    static int order = -1;  // tuning: UNIVL_FA_ORDER=0 (default) contiguous item ranges, 1 synchronised heads (measured 8% slower)
+    if (order < 0) {
+      const char* e = getenv("UNIVL_FA_ORDER");
+      order = e ? atoi(e) : 0;
+    }
+    p.item_order = order;
+  }
   CUtensorMap tx, tw, tq;
   int rc;
   if ((rc = make_tmap(&tx, x, p.T, H, ldx, 128))) return rc;        // box {64 k, 128 rows}
-  if ((rc = make_tmap(&tw, wqkv, 3 * H, H, ldw, 64))) return rc;    // box {64 k, 64 weight rows}
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int mc_mode = -1;  // tuning: UNIVL_FA_MULTICAST=0 disables the 2-CTA weight multicast
+  if (mc_mode < 0) {
+    const char* e = getenv("UNIVL_FA_MULTICAST");
+    mc_mode = e ? atoi(e) : 1;
+  }
+  const long long items = (long long)p.n_blocks * heads;
+  const bool mc = mc_mode != 0 && items >= 2LL * sms;   // pairs only pay when every SM has work either way
+  if ((rc = make_tmap(&tw, wqkv, 3 * H, H, ldw, mc ? 32 : 64))) return rc;    // box {64 k, 64 (32) weight rows}
   if (qkv_out != nullptr) {
     if ((rc = make_tmap_epi(&tq, qkv_out, false, p.T, 3 * H, ld_qkv))) return rc;  // box {64 cols, 32 rows}
   } else {
     tq = tx;
   }
-  cudaError_t e = cudaFuncSetAttribute(fused_qkv_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       FA_SMEM_BYTES);
+  auto kern = mc ? fused_qkv_attention_fwd_kernel<true> : fused_qkv_attention_fwd_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention smem attribute: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long items = (long long)p.n_blocks * heads;
-  const int grid = (int)(items < sms ? items : sms);
-  e = launch_kernel(fused_qkv_attention_fwd_kernel, dim3(grid), dim3(FA_THREADS), (size_t)FA_SMEM_BYTES,
-                    (cudaStream_t)stream, tx, tw, tq, p);
+  int grid = (int)(items < sms ? items : sms);
+  if (mc) grid &= ~1;
+  if (p.n_blocks < 2 * sms) p.item_order = 0;  // synchronised heads only pays (and only balances) with many row blocks per CTA
+  e = launch_kernel_cluster(kern, dim3(grid), dim3(FA_THREADS), (size_t)FA_SMEM_BYTES, (cudaStream_t)stream,
+                            mc ? 2 : 1, tx, tw, tq, p);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention launch: %s", cudaGetErrorString(e));
   UNIVL_CHECK_LAUNCH("fused_qkv_attention_fwd");
   return UNIVL_OK;
@@ -788,8 +865,8 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
         uint4 pu0 = make_uint4(0, 0, 0, 0), pu1 = pu0, su0 = pu0, su1 = pu0;
         uint32_t rs[16], rp[16];
         // warp-collective loads (one column address per warp); lanes of other packed sequences ignore the chunk
-        tmem_ld_32x32b_x16(tmem_base + FB_COL_S + lane_base + c, rs);
-        tmem_ld_32x32b_x16(tmem_base + FB_COL_DP + lane_base + c, rp);
+        tmem_ld_32x32b_x16(tb + FB_COL_S + lane_base + c, rs);
+        tmem_ld_32x32b_x16(tb + FB_COL_DP + lane_base + c, rp);
         tmem_ld_wait();
         if (valid && c >= c0 && c < c0 + p.S) {
           const int kc = c - c0;
