@@ -402,7 +402,9 @@ int plan_gemm(int M, int N, int Kc, int epilogue, int block_n, int split_k, Gemm
     // without split-K the tile count alone must fill the SMs; with the atomic epilogue split-K supplies the
     // parallelism, so keep the widest (most smem-bandwidth-efficient) MMA shape
     if (epilogue != EPI_ATOMIC_F32)
-      while (bn > 64 && (long long)m_tiles * ((N + bn - 1) / bn) < 148) bn >>= 1;
+      // (>= 0.9 wave counts as a wave: 144 tiles of 128x256 move 590 KB each through L2, 288 tiles of 128x128 move
+      // 2 x 393 KB per SM — these small-M GEMMs are bound by the per-SM L2 ingress, so fewer bytes per SM wins)
+      while (bn > 64 && (long long)m_tiles * ((N + bn - 1) / bn) < 132) bn >>= 1;
     if (N <= 64) bn = 64;
     else if (N <= 128 && bn > 128) bn = 128;
   }
