@@ -470,7 +470,8 @@ def main():
     ops.fused_qkv_attention_fwd, ops.fused_attention_bwd = timed_fa_fwd, timed_fa_bwd
     two_stream = os.environ.get("UNIVL_TWO_STREAM")
     os.environ["UNIVL_TWO_STREAM"] = "0"   # per-launch durations are only meaningful when kernels do not share the GPU
-    eager_step(dev_batch)                  # untimed: lets the caching allocator settle in this (single-stream) mode
+    if a.profile_steps > 0:
+        eager_step(dev_batch)              # untimed: lets the caching allocator settle in this (single-stream) mode
     torch.cuda.synchronize()
     for v in list(prof.values()) + list(fa.values()):
         v["events"].clear()

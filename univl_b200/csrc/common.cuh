@@ -325,6 +325,19 @@ __device__ __forceinline__ void tc_fence_before_sync() {
 __device__ __forceinline__ void tc_fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// One lane of a fully converged warp (elect.sync).  The MMA-issuing warp runs its loop with ALL lanes (warp-uniform
+// control flow keeps addresses / descriptors in uniform registers) and wraps only the tcgen05.mma / commit instructions
+// in `if (elect_one())`; an `if (lane == 0)` region around the whole loop makes the compiler re-broadcast every operand
+// (ELECT + R2UR per instruction), which measurably throttles the single issuing thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // whole warp; writes the TMEM base address to *smem_slot
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),

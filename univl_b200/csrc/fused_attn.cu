@@ -20,12 +20,12 @@
 //                   the K-major A operand, log-sum-exp -> HBM
 //   5. O = P V      RB/16 tcgen05.mma (M128 N64 K16) into TMEM, drained to the merged-head context rows in HBM.
 // TMEM (512 columns) is split in two halves that alternate between consecutive items: while the CUDA cores drain /
-// softmax item j in one half, the tensor pipe runs the projection of item j+1 in the other; the single MMA-issuing
-// thread interleaves the short S / PV products of item j between projection k-blocks of item j+1 as soon as their
-// operands are ready (mbarrier polling), so the tensor pipe only idles when it is genuinely starved.
+// softmax item j in one half, the tensor pipe runs the projection of item j+1 in the other; the short S / PV products of
+// item j are issued by their own warp as soon as their operands are ready, so they slot in between projection k-blocks
+// and the projection issuer's loop stays as lean as a plain GEMM's.
 //
-// Warp roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain (TMEM lane quarter = warp & 3),
-// warps 6-13 softmax (two per quarter, alternating 16-key chunks).  All synchronisation is mbarrier-based (tcgen05.commit on the MMA side).
+// Warp roles (480 threads): warp 0 TMA producer, warp 1 projection-MMA issuer, warps 2-5 drain (TMEM lane quarter =
+// warp & 3), warps 6-13 softmax (two per quarter, alternating 16-key chunks), warp 14 issuer of the S / PV products.  All synchronisation is mbarrier-based (tcgen05.commit on the MMA side).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -33,7 +33,7 @@
 
 namespace univl {
 
-constexpr int FA_THREADS = 448;   // forward: TMA + MMA + 4 drain + 8 softmax warps
+constexpr int FA_THREADS = 480;   // forward: TMA + projection MMA + 4 drain + 8 softmax warps + core (S / PV) MMA warp
 constexpr int FB_THREADS = 320;   // backward: TMA + MMA + 8 compute warps
 constexpr int FA_STAGES = 3;
 constexpr int FA_KB = 12;                       // 768 / 64 k-blocks
@@ -217,73 +217,63 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------ MMA issuer --------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_proj = make_idesc_bf16(128, 192, false, false);
-      const uint32_t idesc_s = make_idesc_bf16(128, NK, false, false);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
-      const uint32_t sQ = smem_u32(smem + FA_OFF_Q), sK = smem_u32(smem + FA_OFF_K);
-      const uint32_t sV = smem_u32(smem + FA_OFF_V), sP = smem_u32(smem + FA_OFF_P);
-      int core_j = 0, core_stage = 0;  // next S (stage 0) / PV (stage 1) product to issue, in item order
-      auto try_core = [&](bool blocking) -> bool {
-        if (core_j >= n_items) return false;
-        const int b = core_j & 1;
-        const uint32_t half = tmem_base + b * FA_HALF_COLS;
-        if (core_stage == 0) {
-          if (!mbar_poll(qkv_ready, core_j & 1, blocking)) return false;
-          tc_fence_after_sync();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(half, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
-                      idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[b]);
-          core_stage = 1;
-        } else {
-          if (!mbar_poll(&p_ready[b], (core_j >> 1) & 1, blocking)) return false;
-          tc_fence_after_sync();
-          for (int kk = 0; kk < NK / 16; ++kk)  // contraction over keys: P K-major (64-key atoms), V MN-major
-            umma_bf16(half + FA_O_COL, make_smem_desc_sw128(sP + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(sV + kk * 2048, FA_TILE_BYTES, 1024), idesc_pv, kk > 0 ? 1u : 0u);
-          umma_commit(&pv_done[b]);
-          core_stage = 0;
-          ++core_j;
-        }
-        return true;
-      };
-      auto wait_serving = [&](uint64_t* bar, uint32_t parity) {
-        uint32_t spins = 0;
-        while (!mbar_test_wait(bar, parity)) {
-          try_core(false);
-          if (++spins > (1u << 26)) {
-            printf("univl: fused attention MMA wait timed out (block %d)\n", blockIdx.x);
-            __trap();
-          }
-        }
-      };
-      uint32_t it = 0;
-      for (int j = 0; j < n_items; ++j) {
-        const int b = j & 1;
-        wait_serving(&half_free[b], (((uint32_t)j >> 1) & 1) ^ 1);  // O of item j-2 drained out of this half
+    // ------------------------------------------ projection MMA issuer ----------------------------------
+    // all 32 lanes run the (warp-uniform) loop; one elected lane issues the MMAs and their commits
+    constexpr uint32_t idesc_proj = make_idesc_bf16(128, 192, false, false);
+    uint32_t it = 0;
+    for (int j = 0; j < n_items; ++j) {
+      const int b = j & 1;
+      mbar_wait(&half_free[b], (((uint32_t)j >> 1) & 1) ^ 1);  // O of item j-2 drained out of this half
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + b * FA_HALF_COLS;
+      for (int kb = 0; kb < FA_KB; ++kb, ++it) {
+        const int s = it % FA_STAGES;
+        const uint32_t ph = (it / FA_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + b * FA_HALF_COLS;
-        for (int kb = 0; kb < FA_KB; ++kb, ++it) {
-          try_core(false);
-          const int s = it % FA_STAGES;
-          const uint32_t ph = (it / FA_STAGES) & 1;
-          wait_serving(&full_bar[s], ph);
-          tc_fence_after_sync();
-          const uint32_t sx = smem_u32(smem + s * FA_STAGE_BYTES);
-          const uint32_t sw = sx + FA_X_BYTES;
+        const uint32_t sx = smem_u32(smem + s * FA_STAGE_BYTES);
+        const uint64_t dx0 = make_smem_desc_sw128(sx, 16, 1024);
+        const uint64_t dw0 = make_smem_desc_sw128(sx + FA_X_BYTES, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, make_smem_desc_sw128(sx + k * 32, 16, 1024), make_smem_desc_sw128(sw + k * 32, 16, 1024),
-                      idesc_proj, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)   // +32 bytes per K = 16 step: +2 in the descriptor's 16-byte address field
+            umma_bf16(d_tmem, dx0 + 2 * k, dw0 + 2 * k, idesc_proj, (kb > 0 || k > 0) ? 1u : 0u);
           if (MC) umma_commit_mc(&empty_bar[s], (uint16_t)3);
           else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full[b]);
+        __syncwarp();
       }
-      while (core_j < n_items) try_core(true);
+      if (elect_one()) umma_commit(&acc_full[b]);
+      __syncwarp();
+    }
+  } else if (warp == 14) {
+    // ------------------------------------------ core MMA issuer (S = Q K^T, O = P V) --------------------
+    // a separate warp, so the projection issuer never polls: each product waits (sleeping) for its operands
+    const uint32_t idesc_s = make_idesc_bf16(128, NK, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+    const uint64_t dq0 = make_smem_desc_sw128(smem_u32(smem + FA_OFF_Q), 16, 1024);
+    const uint64_t dk0 = make_smem_desc_sw128(smem_u32(smem + FA_OFF_K), 16, 1024);
+    const uint32_t sV = smem_u32(smem + FA_OFF_V), sP = smem_u32(smem + FA_OFF_P);
+    for (int j = 0; j < n_items; ++j) {
+      const int b = j & 1;
+      const uint32_t half = tmem_base + b * FA_HALF_COLS;
+      mbar_wait(qkv_ready, (uint32_t)j & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(half, dq0 + 2 * k, dk0 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+      mbar_wait(&p_ready[b], ((uint32_t)j >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        for (int kk = 0; kk < NK / 16; ++kk)  // contraction over keys: P K-major (64-key atoms), V MN-major
+          umma_bf16(half + FA_O_COL, make_smem_desc_sw128(sP + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(sV + kk * 2048, FA_TILE_BYTES, 1024), idesc_pv, kk > 0 ? 1u : 0u);
+        umma_commit(&pv_done[b]);
+      }
+      __syncwarp();
     }
   } else if (warp < 6) {
     // ------------------------------------------ drain warps -------------------------------------------
@@ -386,7 +376,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       }
     }
     if (p.store_qkv && lane == 0) bulk_wait_read<0>();
-  } else {
+  } else if (warp < 14) {
     // ------------------------------------------ softmax warps -----------------------------------------
     // Two warps per TMEM lane quarter; a thread owns one query row and every other 16-key chunk (chunk parity = which
     // warp of the pair), holds its <= 64 logits in registers (one TMEM read, one exp per element), and the pair combines

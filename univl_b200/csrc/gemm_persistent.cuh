@@ -352,34 +352,38 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
-      uint32_t it = 0, t = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
-        const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_M, BLOCK_N);
-        const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
+    // All 32 lanes run the warp-uniform loop (addresses and descriptors stay in uniform registers); one elected lane
+    // issues the MMAs and the commits.  (An `if (lane == 0)` around the loop costs an ELECT + R2UR re-broadcast per
+    // operand of every tcgen05 instruction.)
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    uint32_t it = 0, t = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++t) {
+      const WorkItem wi = decode_work(w, m_tiles, n_tiles, total_kb, kb_per, BLOCK_M, BLOCK_N);
+      const uint32_t acc = t & 1, acc_ph = (t >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int i = 0; i < wi.num_kb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int i = 0; i < wi.num_kb; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        // K = 16 step k: K-major operands advance 32 bytes (+2 in the descriptor's 16-byte address field), MN-major
+        // operands 16 rows of 128 bytes (+128)
+        const uint64_t da0 = A_MN ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t db0 = B_MN ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BLOCK_K * 128, 1024)
-                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BLOCK_K * 128, 1024)
-                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, da0 + (A_MN ? 128 : 2) * k, db0 + (B_MN ? 128 : 2) * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+      __syncwarp();
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
@@ -565,7 +569,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-    if (leader && lane == 0) {
+    if (leader) {   // warp-uniform loop, one elected lane issues (see the 1-CTA kernel)
       constexpr uint32_t idesc = make_idesc_bf16(PAIR_M, BLOCK_N, A_MN, B_MN);
       uint32_t it = 0, t = 0;
       for (int w = pair; w < num_work; w += num_pairs, ++t) {
@@ -581,17 +585,19 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          const uint64_t da0 = A_MN ? make_smem_desc_sw128(sa, BLOCK_K * 128, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db0 = B_MN ? make_smem_desc_sw128(sb, BLOCK_K * 128, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BLOCK_K * 128, 1024)
-                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BLOCK_K * 128, 1024)
-                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16_2sm(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_2sm(d_tmem, da0 + (A_MN ? 128 : 2) * k, db0 + (B_MN ? 128 : 2) * k, idesc,
+                            (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[s]);
           }
-          umma_commit_2sm(&empty_bar[s]);
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full_bar[acc]);
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc]);
+        __syncwarp();
       }
     }
   } else {
