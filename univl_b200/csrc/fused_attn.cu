@@ -72,7 +72,14 @@ struct FusedAttnParams {
   int store_qkv;
   int item_order;
   int x_box_rows;   // rows of the x TMA box: RB when RB % 32 == 0 (see the launcher), else 128
+  long long* trace; // bring-up only: per-phase clock64 stamps of CTA 0 (tests/gpu_checks/trace_fused_attn.py), else null
 };
+
+// bring-up instrumentation: event e of item j of CTA 0 (first 16 items)
+#define FA_TRACE(e, j)                                                                          \
+  do {                                                                                          \
+    if (p.trace != nullptr && blockIdx.x == 0 && (j) < 16 && lane == 0) p.trace[(j) * 16 + (e)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity, bool blocking) {
   if (!blocking) return mbar_test_wait(bar, parity) != 0;
@@ -225,6 +232,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       const int b = j & 1;
       mbar_wait(&half_free[b], (((uint32_t)j >> 1) & 1) ^ 1);  // O of item j-2 drained out of this half
       tc_fence_after_sync();
+      FA_TRACE(0, j);
       const uint32_t d_tmem = tmem_base + b * FA_HALF_COLS;
       for (int kb = 0; kb < FA_KB; ++kb, ++it) {
         const int s = it % FA_STAGES;
@@ -245,6 +253,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       }
       if (elect_one()) umma_commit(&acc_full[b]);
       __syncwarp();
+      FA_TRACE(1, j);
     }
   } else if (warp == 14) {
     // ------------------------------------------ core MMA issuer (S = Q K^T, O = P V) --------------------
@@ -259,6 +268,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       const uint32_t half = tmem_base + b * FA_HALF_COLS;
       mbar_wait(qkv_ready, (uint32_t)j & 1);
       tc_fence_after_sync();
+      FA_TRACE(4, j);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(half, dq0 + 2 * k, dk0 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
@@ -267,6 +277,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       __syncwarp();
       mbar_wait(&p_ready[b], ((uint32_t)j >> 1) & 1);
       tc_fence_after_sync();
+      FA_TRACE(7, j);
       if (elect_one()) {
         for (int kk = 0; kk < NK / 16; ++kk)  // contraction over keys: P K-major (64-key atoms), V MN-major
           umma_bf16(half + FA_O_COL, make_smem_desc_sw128(sP + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
@@ -289,6 +300,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
         mbar_wait(&pv_done[b], ((uint32_t)j >> 1) & 1);
         tc_fence_after_sync();
+        if (q == 0) FA_TRACE(8, j);
         const uint32_t t_o = tmem_base + b * FA_HALF_COLS + FA_O_COL + lane_base;
         uint32_t r[4][16];
 #pragma unroll
@@ -314,6 +326,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         }
         tc_fence_before_sync();
         __syncwarp();
+        if (q == 0) FA_TRACE(9, j);
         if (lane == 0) mbar_arrive(&half_free[b]);
       }
       if (jj < n_items) {
@@ -324,10 +337,12 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
         mbar_wait(&acc_full[b], ((uint32_t)j >> 1) & 1);
         tc_fence_after_sync();
+        if (q == 0) FA_TRACE(2, j);
         if (p.store_qkv && jj >= 1) {
           if (lane == 0) bulk_wait_read<0>();  // the bulk stores of item jj-1 have read this warp's tile rows
           __syncwarp();
         }
+        if (q == 0) FA_TRACE(10, j);
         const uint32_t t_acc = tmem_base + b * FA_HALF_COLS + lane_base;
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
@@ -371,6 +386,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
               tma_store_2d(&tmap_qkv, smem + FA_OFF_Q + m * FA_TILE_BYTES + q * 4096, m * p.heads * 64 + h * 64, r0);
             bulk_commit();
           }
+          if (q == 0) FA_TRACE(3, j);
           mbar_arrive(qkv_ready);
         }
       }
@@ -423,6 +439,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       }
       mbar_wait(&s_full[b], ((uint32_t)j >> 1) & 1);
       tc_fence_after_sync();
+      if (warp == 6) FA_TRACE(5, j);
       const long long seq = (long long)rb * p.G + g;
       const bool valid = row < p.RB && seq < p.n_seq;
       const uint32_t t_s = tmem_base + b * FA_HALF_COLS + lane_base;
@@ -509,6 +526,7 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
+      if (warp == 6) FA_TRACE(6, j);
       if (lane == 0) mbar_arrive(&p_ready[b]);
     }
   }
@@ -525,6 +543,14 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
 }  // namespace univl
 
 using namespace univl;
+
+// bring-up only (not part of include/univl_b200.h): device buffer of 16 x 16 int64 that CTA 0 of the next forward launches
+// fills with per-phase clock64 stamps
+static long long* g_fa_trace = nullptr;
+extern "C" int univl_debug_set_fused_attention_trace(void* device_buffer) {
+  g_fa_trace = reinterpret_cast<long long*>(device_buffer);
+  return UNIVL_OK;
+}
 
 // 1 if univl_fused_qkv_attention_fwd supports this shape (else the caller uses the unfused QKV GEMM + attention core)
 extern "C" int univl_fused_qkv_attention_supported(int n_seq, int heads, int S, int H) {
@@ -568,6 +594,7 @@ extern "C" int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const
   p.drop_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   p.rng = rng_state; p.stream = stream_id;
   p.store_qkv = qkv_out != nullptr;
+  p.trace = g_fa_trace;
   {
     static int order = -1;  // tuning: UNIVL_FA_ORDER=0 (default) contiguous item ranges, 1 synchronised heads (measured 8% slower)
     if (order < 0) {
@@ -746,50 +773,57 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
     }
   } else if (warp == 1) {
     // ------------------------------------------ MMA issuer --------------------------------------------
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, NK, false, false);
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
-      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
-      const uint32_t sP = smem_u32(smem + FB_OFF_P), sdS = smem_u32(smem + FB_OFF_DS);
-      // S = Q K^T and dP = dO V^T of item j into TMEM buffer j & 1 (free once the gradients of item j-2 are drained)
-      auto issue_sdp = [&](int j) {
-        const int b = j & 1;
-        const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES), sK = sQ + FA_TILE_BYTES, sV = sK + FA_TILE_BYTES,
-                       sdO = sV + FA_TILE_BYTES;
-        const uint32_t tb = tmem_base + b * FB_BUF_COLS;
-        mbar_wait(&in_full[b], ((uint32_t)j >> 1) & 1);
-        mbar_wait(&acc_free[b], (((uint32_t)j >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
+    // warp-uniform loop, one elected lane issues (see elect_one in common.cuh)
+    const uint32_t idesc_s = make_idesc_bf16(128, NK, false, false);
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);
+    const uint32_t sP = smem_u32(smem + FB_OFF_P), sdS = smem_u32(smem + FB_OFF_DS);
+    const uint64_t dP_mn = make_smem_desc_sw128(sP, FA_TILE_BYTES, 1024);     // P~ as MN-major A (dV)
+    const uint64_t dS_mn = make_smem_desc_sw128(sdS, FA_TILE_BYTES, 1024);    // dS as MN-major A (dK)
+    // S = Q K^T and dP = dO V^T of item j into TMEM buffer j & 1 (free once the gradients of item j-2 are drained)
+    auto issue_sdp = [&](int j) {
+      const int b = j & 1;
+      const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES);
+      const uint64_t dQ = make_smem_desc_sw128(sQ, 16, 1024), dK = make_smem_desc_sw128(sQ + FA_TILE_BYTES, 16, 1024);
+      const uint64_t dV = make_smem_desc_sw128(sQ + 2 * FA_TILE_BYTES, 16, 1024);
+      const uint64_t dO = make_smem_desc_sw128(sQ + 3 * FA_TILE_BYTES, 16, 1024);
+      const uint32_t tb = tmem_base + b * FB_BUF_COLS;
+      mbar_wait(&in_full[b], ((uint32_t)j >> 1) & 1);
+      mbar_wait(&acc_free[b], (((uint32_t)j >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tb + FB_COL_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
-                    make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tb + FB_COL_S, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tb + FB_COL_DP, make_smem_desc_sw128(sdO + k * 32, 16, 1024),
-                    make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tb + FB_COL_DP, dO + 2 * k, dV + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&sd_full[b]);
-      };
-      if (n_items > 0) issue_sdp(0);
-      for (int j = 0; j < n_items; ++j) {
-        const int b = j & 1;
-        const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES), sK = sQ + FA_TILE_BYTES, sdO = sK + 2 * FA_TILE_BYTES;
-        const uint32_t tb = tmem_base + b * FB_BUF_COLS;
-        if (j + 1 < n_items) issue_sdp(j + 1);   // runs while the compute warps work on item j
-        mbar_wait(pds_ready, (uint32_t)j & 1);
-        tc_fence_after_sync();
-        for (int kk = 0; kk < NK / 16; ++kk)  // dQ[q, d] = sum_key dS[q, key] K[key, d]
+      }
+      __syncwarp();
+    };
+    if (n_items > 0) issue_sdp(0);
+    for (int j = 0; j < n_items; ++j) {
+      const int b = j & 1;
+      const uint32_t sQ = smem_u32(smem + b * FB_IN_BYTES);
+      const uint64_t dQ_mn = make_smem_desc_sw128(sQ, FA_TILE_BYTES, 1024);                       // Q as MN-major B (dK)
+      const uint64_t dK_mn = make_smem_desc_sw128(sQ + FA_TILE_BYTES, FA_TILE_BYTES, 1024);       // K as MN-major B (dQ)
+      const uint64_t dO_mn = make_smem_desc_sw128(sQ + 3 * FA_TILE_BYTES, FA_TILE_BYTES, 1024);   // dO as MN-major B (dV)
+      const uint32_t tb = tmem_base + b * FB_BUF_COLS;
+      if (j + 1 < n_items) issue_sdp(j + 1);   // runs while the compute warps work on item j
+      mbar_wait(pds_ready, (uint32_t)j & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        for (int kk = 0; kk < NK / 16; ++kk)  // dQ[q, d] = sum_key dS[q, key] K[key, d]   (16 keys = +128 in MN-major K)
           umma_bf16(tb + FB_COL_DQ, make_smem_desc_sw128(sdS + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(sK + kk * 2048, FA_TILE_BYTES, 1024), idesc_dq, kk > 0 ? 1u : 0u);
+                    dK_mn + 128 * kk, idesc_dq, kk > 0 ? 1u : 0u);
+#pragma unroll
         for (int kk = 0; kk < 8; ++kk) {      // contraction over the 128 query rows of the tile (rows >= RB hold zeros)
-          umma_bf16(tb + FB_COL_DV, make_smem_desc_sw128(sP + kk * 2048, FA_TILE_BYTES, 1024),
-                    make_smem_desc_sw128(sdO + kk * 2048, FA_TILE_BYTES, 1024), idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(tb + FB_COL_DK, make_smem_desc_sw128(sdS + kk * 2048, FA_TILE_BYTES, 1024),
-                    make_smem_desc_sw128(sQ + kk * 2048, FA_TILE_BYTES, 1024), idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(tb + FB_COL_DV, dP_mn + 128 * kk, dO_mn + 128 * kk, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(tb + FB_COL_DK, dS_mn + 128 * kk, dQ_mn + 128 * kk, idesc_t, kk > 0 ? 1u : 0u);
         }
         umma_commit(&acc_full[b]);
         umma_commit(&in_empty[b]);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------ compute warps -----------------------------------------
