@@ -45,7 +45,8 @@ constexpr int FA_OFF_Q = FA_STAGES * FA_STAGE_BYTES;
 constexpr int FA_OFF_K = FA_OFF_Q + FA_TILE_BYTES;
 constexpr int FA_OFF_V = FA_OFF_K + FA_TILE_BYTES;
 constexpr int FA_OFF_P = FA_OFF_V + FA_TILE_BYTES;            // two 64-key atoms
-constexpr int FA_OFF_MADD = FA_OFF_P + 2 * FA_TILE_BYTES;     // 128 floats
+constexpr int FA_OFF_V2 = FA_OFF_P + 2 * FA_TILE_BYTES;       // V tile of odd items (V is double-buffered, see the drain warps)
+constexpr int FA_OFF_MADD = FA_OFF_V2 + FA_TILE_BYTES;        // 128 floats
 constexpr int FA_OFF_XCH = FA_OFF_MADD + 512;                 // softmax pair exchange: max[2][128], sum[2][128] floats
 constexpr int FA_OFF_BAR = FA_OFF_XCH + 2048;
 // full[3] empty[3] acc_full[2] s_full[2] p_ready[2] pv_done[2] half_free[2] qkv_ready[1]
@@ -262,29 +263,46 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
     const uint64_t dq0 = make_smem_desc_sw128(smem_u32(smem + FA_OFF_Q), 16, 1024);
     const uint64_t dk0 = make_smem_desc_sw128(smem_u32(smem + FA_OFF_K), 16, 1024);
-    const uint32_t sV = smem_u32(smem + FA_OFF_V), sP = smem_u32(smem + FA_OFF_P);
-    for (int j = 0; j < n_items; ++j) {
-      const int b = j & 1;
-      const uint32_t half = tmem_base + b * FA_HALF_COLS;
-      mbar_wait(qkv_ready, (uint32_t)j & 1);
-      tc_fence_after_sync();
-      FA_TRACE(4, j);
-      if (elect_one()) {
+    const uint32_t sV = smem_u32(smem + FA_OFF_V), sV2 = smem_u32(smem + FA_OFF_V2), sP = smem_u32(smem + FA_OFF_P);
+    // S(j) as soon as the Q / K tiles of item j are written, PV(j) as soon as its P is: S(j+1) may overtake PV(j) (they
+    // work in different TMEM halves), which is what lets the projection of item j+2 start on time.
+    int js = 0, jp = 0;
+    uint32_t spins = 0;
+    while (jp < n_items) {
+      bool did = false;
+      if (js < n_items && mbar_test_wait(qkv_ready, (uint32_t)js & 1)) {
+        const uint32_t half = tmem_base + (js & 1) * FA_HALF_COLS;
+        tc_fence_after_sync();
+        FA_TRACE(4, js);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(half, dq0 + 2 * k, dk0 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[b]);
+          for (int k = 0; k < 4; ++k) umma_bf16(half, dq0 + 2 * k, dk0 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[js & 1]);
+        }
+        __syncwarp();
+        ++js;
+        did = true;
       }
-      __syncwarp();
-      mbar_wait(&p_ready[b], ((uint32_t)j >> 1) & 1);
-      tc_fence_after_sync();
-      FA_TRACE(7, j);
-      if (elect_one()) {
-        for (int kk = 0; kk < NK / 16; ++kk)  // contraction over keys: P K-major (64-key atoms), V MN-major
-          umma_bf16(half + FA_O_COL, make_smem_desc_sw128(sP + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(sV + kk * 2048, FA_TILE_BYTES, 1024), idesc_pv, kk > 0 ? 1u : 0u);
-        umma_commit(&pv_done[b]);
+      if (jp < js && mbar_test_wait(&p_ready[jp & 1], ((uint32_t)jp >> 1) & 1)) {
+        const uint32_t half = tmem_base + (jp & 1) * FA_HALF_COLS;
+        const uint32_t sVj = (jp & 1) ? sV2 : sV;
+        tc_fence_after_sync();
+        FA_TRACE(7, jp);
+        if (elect_one()) {
+          for (int kk = 0; kk < NK / 16; ++kk)  // contraction over keys: P K-major (64-key atoms), V MN-major
+            umma_bf16(half + FA_O_COL, make_smem_desc_sw128(sP + (kk >> 2) * FA_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(sVj + kk * 2048, FA_TILE_BYTES, 1024), idesc_pv, kk > 0 ? 1u : 0u);
+          umma_commit(&pv_done[jp & 1]);
+        }
+        __syncwarp();
+        ++jp;
+        did = true;
       }
-      __syncwarp();
+      if (did) spins = 0;
+      else if (++spins > (1u << 26)) {
+        if (lane == 0) printf("univl: fused attention core-MMA wait timed out (block %d)\n", blockIdx.x);
+        __trap();
+      }
     }
   } else if (warp < 6) {
     // ------------------------------------------ drain warps -------------------------------------------
@@ -292,6 +310,71 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
     const int row = q * 32 + lane;          // tile row this thread owns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     for (int jj = 0; jj <= n_items; ++jj) {
+      if (jj < n_items) {
+        // ---- projection accumulators of item jj -> Q / K / V operand tiles.  First thing in the iteration: it gates S(jj).
+        // The Q / K tiles are free once S(jj-1) has read them (s_full); V is double-buffered (item parity), its previous
+        // user PV(jj-2) was waited for by the O drain of the last iteration — so this never waits for PV(jj-1). ----
+        const int j = jj, b = j & 1;
+        int rb, h;
+        items.decode(j, rb, h);
+        if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
+        mbar_wait(&acc_full[b], ((uint32_t)j >> 1) & 1);
+        if (jj >= 1) mbar_wait(&s_full[(jj - 1) & 1], ((uint32_t)(jj - 1) >> 1) & 1);
+        tc_fence_after_sync();
+        if (q == 0) FA_TRACE(2, j);
+        if (p.store_qkv && jj >= 1) {
+          if (lane == 0) bulk_wait_read<0>();  // the bulk stores of item jj-1 have read this warp's tile rows
+          __syncwarp();
+        }
+        if (q == 0) FA_TRACE(10, j);
+        const uint32_t t_acc = tmem_base + b * FA_HALF_COLS + lane_base;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          uint32_t r[4][16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(t_acc + m * 64 + c * 16, r[c]);
+          tmem_ld_wait();
+          const float* bias = p.bias + m * p.heads * 64 + h * 64;
+          uint8_t* trow = smem + (m < 2 ? FA_OFF_Q + m * FA_TILE_BYTES : ((j & 1) ? FA_OFF_V2 : FA_OFF_V)) + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c * 16 + e));
+              v[e] = __uint_as_float(r[c][e]) + bb.x;
+              v[e + 1] = __uint_as_float(r[c][e + 1]) + bb.y;
+              v[e + 2] = __uint_as_float(r[c][e + 2]) + bb.z;
+              v[e + 3] = __uint_as_float(r[c][e + 3]) + bb.w;
+            }
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              uint4 u;
+              u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+              u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+              u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+              u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+              const int chunk = c * 2 + g8;  // 16-byte chunk inside the 128-byte row; XOR swizzle = TMA/UMMA 128B swizzle
+              *reinterpret_cast<uint4*>(trow + ((chunk ^ (row & 7)) << 4)) = u;
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core and the bulk-copy engine
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.store_qkv && q * 32 < p.RB) {
+            const int r0 = rb * p.RB + q * 32;
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+              tma_store_2d(&tmap_qkv, smem + (m < 2 ? FA_OFF_Q + m * FA_TILE_BYTES : ((j & 1) ? FA_OFF_V2 : FA_OFF_V)) + q * 4096,
+                           m * p.heads * 64 + h * 64, r0);
+            bulk_commit();
+          }
+          if (q == 0) FA_TRACE(3, j);
+          mbar_arrive(qkv_ready);
+        }
+      }
       if (jj >= 1) {
         // ---- O of item jj-1 -> merged-head context rows ----
         const int j = jj - 1, b = j & 1;
@@ -328,67 +411,6 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
         __syncwarp();
         if (q == 0) FA_TRACE(9, j);
         if (lane == 0) mbar_arrive(&half_free[b]);
-      }
-      if (jj < n_items) {
-        // ---- projection accumulators of item jj -> Q / K / V operand tiles (Q/K/V/P of item jj-1 are free: pv_done) ----
-        const int j = jj, b = j & 1;
-        int rb, h;
-        items.decode(j, rb, h);
-        if (MC) rb = 2 * rb + crank;   // (an odd tail leaves CTA 1 a block past the end: zero-filled loads, no outputs)
-        mbar_wait(&acc_full[b], ((uint32_t)j >> 1) & 1);
-        tc_fence_after_sync();
-        if (q == 0) FA_TRACE(2, j);
-        if (p.store_qkv && jj >= 1) {
-          if (lane == 0) bulk_wait_read<0>();  // the bulk stores of item jj-1 have read this warp's tile rows
-          __syncwarp();
-        }
-        if (q == 0) FA_TRACE(10, j);
-        const uint32_t t_acc = tmem_base + b * FA_HALF_COLS + lane_base;
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          uint32_t r[4][16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(t_acc + m * 64 + c * 16, r[c]);
-          tmem_ld_wait();
-          const float* bias = p.bias + m * p.heads * 64 + h * 64;
-          uint8_t* trow = smem + FA_OFF_Q + m * FA_TILE_BYTES + row * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float v[16];
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c * 16 + e));
-              v[e] = __uint_as_float(r[c][e]) + bb.x;
-              v[e + 1] = __uint_as_float(r[c][e + 1]) + bb.y;
-              v[e + 2] = __uint_as_float(r[c][e + 2]) + bb.z;
-              v[e + 3] = __uint_as_float(r[c][e + 3]) + bb.w;
-            }
-#pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
-              uint4 u;
-              u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
-              u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
-              u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
-              u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
-              const int chunk = c * 2 + g8;  // 16-byte chunk inside the 128-byte row; XOR swizzle = TMA/UMMA 128B swizzle
-              *reinterpret_cast<uint4*>(trow + ((chunk ^ (row & 7)) << 4)) = u;
-            }
-          }
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core and the bulk-copy engine
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) {
-          if (p.store_qkv && q * 32 < p.RB) {
-            const int r0 = rb * p.RB + q * 32;
-#pragma unroll
-            for (int m = 0; m < 3; ++m)
-              tma_store_2d(&tmap_qkv, smem + FA_OFF_Q + m * FA_TILE_BYTES + q * 4096, m * p.heads * 64 + h * 64, r0);
-            bulk_commit();
-          }
-          if (q == 0) FA_TRACE(3, j);
-          mbar_arrive(qkv_ready);
-        }
       }
     }
     if (p.store_qkv && lane == 0) bulk_wait_read<0>();
@@ -458,11 +480,20 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
           tmem_ld_wait();
           const bool own = valid && c >= c0 && c < c0 + p.S;
           const int kc = c - c0;
+          float a[16];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {   // additive mask of the chunk: four 16-byte shared-memory loads
+            const float4 m4 = *reinterpret_cast<const float4*>(madd + c + e4 * 4);
+            a[e4 * 4] = m4.x; a[e4 * 4 + 1] = m4.y; a[e4 * 4 + 2] = m4.z; a[e4 * 4 + 3] = m4.w;
+          }
+          if (p.causal) {   // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if ((kc + e) > qpos && a[e] == 0.f) a[e] = neg_big;
+          }
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float a = madd[c + e];
-            if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
-            t[i][e] = own ? fmaf(__uint_as_float(r[e]), sl2, a) : -INFINITY;
+            t[i][e] = own ? fmaf(__uint_as_float(r[e]), sl2, a[e]) : -INFINITY;
             mx = fmaxf(mx, t[i][e]);
           }
         }
@@ -488,6 +519,9 @@ fused_qkv_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const
       l = xsum[row] + xsum[128 + row];
       const float inv = valid ? (p.drop_on ? p.drop_scale : 1.0f) / l : 0.f;
       const long long bh = seq * p.heads + h;
+      // the P tile is single-buffered: PV(j-1) must have read it (normally long done — it was issued when this warp
+      // finished item j-1)
+      if (j >= 1) mbar_wait(&pv_done[(j - 1) & 1], ((uint32_t)(j - 1) >> 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = half * 16 + i * 32;
@@ -915,11 +949,20 @@ fused_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
             }
           }
           float pd[16], dsv[16];
+          float a[16];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(madd + c + e4 * 4);
+            a[e4 * 4] = m4.x; a[e4 * 4 + 1] = m4.y; a[e4 * 4 + 2] = m4.z; a[e4 * 4 + 3] = m4.w;
+          }
+          if (p.causal) {   // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if ((kc + e) > qpos && a[e] == 0.f) a[e] = neg_big;
+          }
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float a = madd[c + e];
-            if (p.causal && (kc + e) > qpos && a == 0.f) a = neg_big;
-            const float pr = ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, a) - lse2);
+            const float pr = ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, a[e]) - lse2);
             const bool kp = (keep >> e) & 1u;
             const float gdrop = kp ? __uint_as_float(rp[e]) * ds_scale : 0.f;
             pd[e] = kp ? pr * ds_scale : 0.f;
