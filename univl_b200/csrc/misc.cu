@@ -234,6 +234,11 @@ extern "C" int univl_tanh_bwd_bf16(const void* dy, const void* y, void* out, lon
 extern "C" int univl_fill_f32(float* p, float value, long long n, void* stream) {
   UNIVL_CHECK_ARG(p && n >= 0, "fill: bad arguments");
   if (n == 0) return UNIVL_OK;
+  if (value == 0.0f) {  // gradient-buffer clears (677 MB per step): the runtime's memset path, graph-capturable
+    cudaError_t e = cudaMemsetAsync(p, 0, (size_t)n * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fill memset: %s", cudaGetErrorString(e));
+    return UNIVL_OK;
+  }
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   fill_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, value, n);

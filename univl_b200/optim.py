@@ -22,6 +22,11 @@ def _align(n, a=64):
     return (n + a - 1) // a * a
 
 
+def _zero(flat):
+    """clear a flat fp32 buffer through the C ABI (cudaMemsetAsync on the current stream; capturable)"""
+    call("univl_fill_f32", flat.data_ptr(), 0.0, flat.numel())
+
+
 class FlatParams:
     """Flatten a model's parameters/gradients (idempotent per model)."""
 
@@ -84,7 +89,7 @@ class FlatParams:
         return self.g[off0:off].view((rows,) + shape0[1:])
 
     def zero_grad(self):
-        self.g.zero_()
+        _zero(self.g)
 
 
 def flatten(model, sink_grads=True):
@@ -242,7 +247,7 @@ class FusedBertAdam(torch.optim.Optimizer):
         addition to the private flat copy."""
         if not self._built:
             return super(FusedBertAdam, self).zero_grad(set_to_none=set_to_none)
-        self.g.zero_()
+        _zero(self.g)
         if self.flat is not None:
             for p, off in zip(self.flat.params, self.flat.offsets):
                 if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + 4 * off:
