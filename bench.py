@@ -401,23 +401,49 @@ def main():
     # ---- timed region 2: end to end from pinned host buffers (H2D of inputs + D2H of the loss every step) ----
     e2e = None
     if not a.no_e2e:
-        def h2d():
-            # graph mode: copy straight into the graph's static input buffers; eager: fresh device tensors
-            return host_batch if graphed else {k: v.to(dev, non_blocking=True) for k, v in host_batch.items()}
-        # the loss of every step is read back into pinned host memory by an asynchronous D2H copy on the step's
-        # stream (what a training loop that logs the loss does); the host synchronises once, after the last step, so
-        # host-side jitter queues behind the device instead of stalling it (a per-step float() made this leg swing
-        # between 12.3 and 16.3 ms/step with the load on the box's CPUs)
+        # The loss of every step is read back into pinned host memory by an asynchronous D2H copy on the step's stream
+        # (what a training loop that logs the loss does); the host synchronises once, after the last step, so host-side
+        # jitter queues behind the device instead of stalling it.
+        # The inputs of step i+1 are prefetched while step i computes, as any input pipeline does: H2D from the pinned
+        # host batch into one of two staging sets on a copy stream, then a device-to-device copy into the graph's static
+        # input tensors at the head of the step.  Every step still moves all its input bytes host -> device and its loss
+        # device -> host inside the timed region.
         loss_host = torch.zeros(a.steps + 2, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream()
+        stage_sets = [{k: torch.empty_like(v) for k, v in dev_batch.items()} for _ in range(2)]
+        staged = [torch.cuda.Event(), torch.cuda.Event()]      # H2D into set s finished
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]    # set s copied out by the compute stream
+        for ev in consumed:
+            ev.record(torch.cuda.current_stream())
 
-        def e2e_step(i):
-            loss_host[i:i + 1].copy_(step(h2d()).detach().reshape(1), non_blocking=True)
+        def prefetch(i):
+            s_ = i % 2
+            copy_stream.wait_event(consumed[s_])
+            with torch.cuda.stream(copy_stream):
+                for k, v in host_batch.items():
+                    stage_sets[s_][k].copy_(v, non_blocking=True)
+                staged[s_].record(copy_stream)
+
+        def e2e_step(i, slot):
+            s_ = i % 2
+            cur = torch.cuda.current_stream()
+            cur.wait_event(staged[s_])
+            if graphed:
+                for k, v in stage_sets[s_].items():
+                    dev_batch[k].copy_(v, non_blocking=True)
+                batch = dev_batch
+            else:
+                batch = {k: v.clone() for k, v in stage_sets[s_].items()}
+            consumed[s_].record(cur)
+            prefetch(i + 1)
+            loss_host[slot:slot + 1].copy_(step(batch).detach().reshape(1), non_blocking=True)
+        prefetch(0)
         for i in range(2):
-            e2e_step(a.steps + i)
+            e2e_step(i, a.steps + i)
         barrier()
         e0.record()
         for i in range(a.steps):
-            e2e_step(i)
+            e2e_step(i + 2, i)
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1) / a.steps
