@@ -36,17 +36,26 @@ class FlatGradReducer:
     def grad_scale(self):
         return 1.0 / self.world
 
-    def pack(self):
-        """fp32 gradients -> bf16 payload (no-op without compression / single process)"""
+    def pack(self, ranges=None):
+        """fp32 gradients -> bf16 payload (no-op without compression / single process); `ranges`: only these [a, b)"""
         if self.compress is None or self.world == 1:
             return
         if self.payload is None:
             self.payload = torch.empty(self.g.numel(), dtype=torch.bfloat16, device=self.g.device)
-        if self.g.is_cuda:
-            from .runtime import call
-            call("univl_cast_f32_to_bf16", self.g.data_ptr(), self.payload.data_ptr(), self.g.numel())
-        else:
-            self.payload.copy_(self.g)   # gloo logic tests on CPU tensors
+        for a, b in (ranges if ranges is not None else [(0, self.g.numel())]):
+            if self.g.is_cuda:
+                from .runtime import call
+                call("univl_cast_f32_to_bf16", self.g[a:b].data_ptr(), self.payload[a:b].data_ptr(), b - a)
+            else:
+                self.payload[a:b].copy_(self.g[a:b])   # gloo logic tests on CPU tensors
+
+    def all_reduce_ranges(self, ranges, async_op=True):
+        """sum-reduce the given [a, b) runs of the payload (bf16) or of the gradient buffer; returns the work handles"""
+        if self.world == 1:
+            return []
+        buf = self.payload if self.compress is not None else self.g
+        return [dist.all_reduce(buf[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+                for a, b in ranges]
 
     def unpack(self):
         """summed bf16 payload -> fp32 gradient buffer"""
@@ -76,3 +85,64 @@ class FlatGradReducer:
         if self.compress is not None and not packed and not async_op:
             self.unpack()
         return works
+
+
+class PhasedBackward:
+    """Backward in two phases so the gradient exchange of phase 1 overlaps the compute of phase 2.
+
+    The reference's DDP overlaps bucketed all-reduces with the rest of backward through autograd hooks
+    (main_task_retrieval.py:197-198).  Here the step is replayed from CUDA graphs, which cannot contain the NCCL calls,
+    so the backward is cut at one tensor instead: the hidden state entering text-encoder layer `split_layer`.
+      phase 1  loss -> cross encoder -> visual encoder (side stream) and text layers 11 .. split_layer
+               => every gradient of the cross / visual / similarity parameters and of the upper text layers is final
+      phase 2  text layers split_layer-1 .. 0 and the text embeddings
+    `phase1_ranges` / `phase2_ranges` are the contiguous runs of the flat gradient buffer each phase completes, so the
+    caller can all-reduce the first set while phase 2 runs (bench.py).  Needs the flat layout (`FusedBertAdam(model=)`).
+    """
+
+    def __init__(self, model, flat, split_layer):
+        self.model, self.flat = model, flat
+        self.split_layer = int(split_layer)
+        stack = model.bert.encoder
+        if not 0 < self.split_layer < len(stack.layer):
+            raise ValueError("PhasedBackward: split_layer must be inside the text stack")
+        stack.__dict__["_split_at"] = self.split_layer
+        late = set()
+        for name, p in model.named_parameters():
+            if name.startswith("bert.embeddings."):
+                late.add(id(p))
+            elif name.startswith("bert.encoder.layer."):
+                if int(name.split(".")[3]) < self.split_layer:
+                    late.add(id(p))
+        # tied tables (decoder / MLM heads share the word table) receive gradients in phase 1 too: they complete in phase 2
+        self.phase2_ranges = self._runs([p for p in flat.params if id(p) in late])
+        self.phase1_ranges = self._runs([p for p in flat.params if id(p) not in late])
+        # leaves at the far end of each phase's sub-graph: asking autograd for their gradients makes it run the whole
+        # branch (the kernels accumulate into the flat buffer themselves and hand autograd None)
+        self._far1 = [model.visual.embeddings.position_embeddings.weight, model.normalize_video.visual_norm2d.weight]
+        self._far2 = [model.bert.embeddings.word_embeddings.weight]
+        self._g_split = None
+
+    def _runs(self, params):
+        segs = sorted((self.flat.by_id[id(p)][0], self.flat.by_id[id(p)][1]) for p in params)
+        runs = []
+        for off, n in segs:
+            end = off + (n + 63) // 64 * 64
+            if runs and off <= runs[-1][1]:
+                runs[-1][1] = max(runs[-1][1], end)
+            else:
+                runs.append([off, end])
+        total = self.flat.total
+        return [(a, min(b, total)) for a, b in runs]
+
+    def phase1(self, loss):
+        split = self.model.bert.encoder.__dict__.get("_split_tensor")
+        if split is None:
+            raise RuntimeError("PhasedBackward: the text encoder did not run in this forward")
+        grads = torch.autograd.grad(loss, [split] + self._far1, allow_unused=True)
+        self._split, self._g_split = split, grads[0]
+
+    def phase2(self):
+        torch.autograd.grad([self._split], self._far2, grad_outputs=[self._g_split], allow_unused=True)
+        self._split = self._g_split = None
+        self.model.bert.encoder.__dict__.pop("_split_tensor", None)

@@ -116,7 +116,10 @@ class EncoderStack(nn.Module):
 
     def run(self, x2d, n_seq, S, mask, keep_all=False):
         outs = []
-        for layer in self.layer:
+        split_at = self.__dict__.get("_split_at")   # univl_b200.ddp.PhasedBackward: remember the input of this layer
+        for i, layer in enumerate(self.layer):
+            if split_at is not None and i == split_at and x2d.requires_grad:
+                self.__dict__["_split_tensor"] = x2d
             x2d = layer.run(x2d, n_seq, S, mask)
             if keep_all:
                 outs.append(x2d)
