@@ -27,6 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+AUTO_CUTS = "off"   # measured: no gain at N=2 (the all-reduce under the backward slows it by what it hides), see DESIGN.md
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -46,6 +49,11 @@ def parse():
     ap.add_argument("--profile_steps", type=int, default=2)
     ap.add_argument("--grad_payload", default="bf16", choices=["bf16", "f32"],
                     help="N > 1: dtype of the gradient all-reduce payload (bf16 halves the NVLink bytes)")
+    ap.add_argument("--overlap_cuts", default="auto", help="N > 1: text-encoder layers at which the backward is cut into "
+                    "phases whose gradient all-reduce overlaps the next phase (univl_b200.ddp.PhasedBackward), e.g. "
+                    "'9,5'; '' or 'off' = one all-reduce after the whole backward; auto = " + AUTO_CUTS)
+    ap.add_argument("--overlap_sms", type=int, default=0, help="SMs left to the overlapped all-reduce: NCCL_MAX_CTAS and "
+                    "the reservation the persistent kernels of the overlapped phases size their grids for")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (falls back to eager "
                     "launches if capture fails), 0: eager")
     return ap.parse_args()
@@ -255,7 +263,7 @@ def main():
     import torch.distributed as dist
     from oracle import synth
     from univl_b200 import ops, runtime as rt
-    from univl_b200.ddp import FlatGradReducer
+    from univl_b200.ddp import FlatGradReducer, PhasedBackward
     from univl_b200.optim import FusedBertAdam
     from tests.model_util import bert_dir
 
@@ -266,7 +274,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cuts = AUTO_CUTS if a.overlap_cuts == "auto" else a.overlap_cuts
+    overlap = world > 1 and a.graph and cuts not in ("", "off", "0")
     if world > 1:
+        if overlap and a.overlap_sms > 0:
+            # the all-reduce that runs under the next backward phase gets a fixed SM allowance; the phase's persistent
+            # kernels are launched on the remaining SMs (univl_set_reserved_sms) instead of queueing a second wave
+            os.environ.setdefault("NCCL_MAX_CTAS", str(a.overlap_sms))
         dist.init_process_group("nccl", device_id=dev)
 
     from univl_b200.modules.modeling import UniVL
@@ -293,6 +307,12 @@ def main():
                         grad_scale=1.0 / world, model=model)
     opt._build()
     reducer = FlatGradReducer(opt.p, opt.g, n_buckets=4, compress="bf16" if a.grad_payload == "bf16" else None)
+    phased = None
+    if overlap:
+        n_text = len(model.bert.encoder.layer)
+        cut_layers = [int(c) for c in cuts.split(",") if 0 < int(c) < n_text]
+        if cut_layers:
+            phased = PhasedBackward(model, opt.flat, cut_layers)
 
     host_batch = synth.make_batch(cfg, seed=1234 + rank, b=a.batch)
     host_batch = {k: v.pin_memory() for k, v in host_batch.items()}
@@ -301,8 +321,15 @@ def main():
 
     def fwd_bwd(batch):
         opt.zero_grad()
+        if phased is not None:
+            phased.begin()
         loss = model(**batch)
-        loss.backward()
+        if phased is not None:
+            phased.backward(0, loss)
+            for ph in range(1, phased.n_phases):
+                phased.backward(ph)
+        else:
+            loss.backward()
         return loss
 
     def step(batch):
@@ -343,32 +370,76 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             n0 = rt.launch_count()
-            # N > 1: the NCCL all-reduce stays an eager call between two graphs (forward+backward | optimizer)
+            # N > 1: the NCCL all-reduce stays an eager call between graphs.  Without phases: forward+backward | all-reduce
+            # | optimizer.  With phases: forward + backward phase 0 | async all-reduce of phase 0's finished gradient runs
+            # || backward phase 1 | async all-reduce of phase 1's runs || ... | wait | optimizer -- the exchange of one
+            # phase rides under the compute of the next (what DDP's bucket hooks do in the reference).
             graph = torch.cuda.CUDAGraph()
             graph_opt = None
+            phase_graphs = []
             with torch.cuda.graph(graph):
                 if world == 1:
                     static_loss = eager_step(static_batch)
-                else:
+                elif phased is None:
                     static_loss = fwd_bwd(static_batch)
                     reducer.pack()          # fp32 gradients -> bf16 payload, inside the backward graph
+                else:
+                    opt.zero_grad()
+                    phased.begin()
+                    static_loss = model(**static_batch)
+                    phased.backward(0, static_loss)
+                    reducer.pack(phased.ranges[0])
+            if phased is not None:
+                for ph in range(1, phased.n_phases):
+                    g_ph = torch.cuda.CUDAGraph()
+                    rt.reserve_sms(a.overlap_sms)   # this phase shares the GPU with an all-reduce
+                    try:
+                        with torch.cuda.graph(g_ph, pool=graph.pool()):
+                            phased.backward(ph)
+                            reducer.pack(phased.ranges[ph])
+                    finally:
+                        rt.reserve_sms(0)
+                    phase_graphs.append(g_ph)
             if world > 1:
                 graph_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph_opt):
-                    reducer.unpack()        # summed payload -> fp32 gradient buffer
+                with torch.cuda.graph(graph_opt, pool=graph.pool()):
+                    if reducer.compress is not None:
+                        opt.grad_payload = reducer.payload   # the optimizer reads the summed bf16 payload directly
                     opt.step()
+                    opt.grad_payload = None
             launches_per_step = rt.launch_count() - n0
             torch.cuda.synchronize()
             stage("graphs captured")
 
-            def step(batch):
+            def step(batch, marks=None):
+                def mark(tag):
+                    if marks is not None:
+                        ev = torch.cuda.Event(enable_timing=True)
+                        ev.record()
+                        marks.append((tag, ev))
                 if batch is not static_batch:
                     for k, v in batch.items():
                         static_batch[k].copy_(v, non_blocking=True)
+                mark("start")
                 graph.replay()
-                if graph_opt is not None:
-                    reducer.all_reduce(packed=True)
+                if phased is not None:
+                    mark("forward + backward phase 0")
+                    works = reducer.all_reduce_ranges(phased.ranges[0])
+                    for ph, g_ph in enumerate(phase_graphs, 1):
+                        g_ph.replay()
+                        mark("backward phase %d (under the all-reduce of phase %d)" % (ph, ph - 1))
+                        works += reducer.all_reduce_ranges(phased.ranges[ph])
+                    for w in works:
+                        w.wait()
+                    mark("exposed all-reduce")
                     graph_opt.replay()
+                    mark("optimizer")
+                elif graph_opt is not None:
+                    mark("forward + backward")
+                    reducer.all_reduce(packed=True)
+                    mark("all-reduce")
+                    graph_opt.replay()
+                    mark("optimizer")
                 return static_loss
             for _ in range(2):
                 step(static_batch)
@@ -397,6 +468,19 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     launches = (launches_per_step * a.steps) if graphed else (rt.launch_count() - launches0)
     loss_val = float(loss.detach())
+
+    # where a multi-GPU step goes (rank 0's device clock, 5 extra steps outside the timed region)
+    breakdown = None
+    if world > 1 and graphed:
+        acc = {}
+        for _ in range(5):
+            marks = []
+            step(dev_batch, marks)
+            torch.cuda.synchronize()
+            for (_, e_a), (tag, e_b) in zip(marks[:-1], marks[1:]):
+                acc[tag] = acc.get(tag, 0.0) + e_a.elapsed_time(e_b) / 5
+        breakdown = acc
+        barrier()
 
     # ---- timed region 2: end to end from pinned host buffers (H2D of inputs + D2H of the loss every step) ----
     e2e = None
@@ -557,10 +641,13 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": samples, "parallelism": "dp%d" % world,
                    "dropout": a.dropout, "optimizer": "fused BertAdam + clip (in timed region)",
-                   "grad_allreduce": ("NCCL sum, %s payload, after backward" % a.grad_payload) if world > 1 else "none",
+                   "grad_allreduce": "none" if world == 1 else ("NCCL sum, %s payload, %s" % (
+                       a.grad_payload, "after backward" if phased is None or not graphed else
+                       "overlapped with backward: %d phases cut at text layers %s" % (phased.n_phases, phased.cuts))),
                    "launch": "cuda-graph replay" if graphed else "eager",
                    "l2": "per-step working set (~6 GB of activations at FT-Align b=32) exceeds the 126 MB L2"},
         "gpu_launches": launches, "loss": loss_val,
+        **({"step_breakdown_ms": breakdown} if breakdown else {}),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "kernel": "gemm_tcgen05_2cta_kernel" if per[2]["n"] else "gemm_tcgen05_persistent_kernel",

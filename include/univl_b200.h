@@ -22,6 +22,11 @@ extern "C" {
 
 const char* univl_last_error_string(void);
 int univl_abi_version(void);
+/* Number of SMs a concurrent collective kernel (NCCL all-reduce on another stream) occupies while the kernels enqueued
+ * from now on run; persistent grids (GEMM, fused attention) are sized to the remaining SMs / SM pairs.  0 = none
+ * (default).  Process-wide; read at enqueue time (captured graphs keep their grids).
+ * No reference counterpart: DDP's overlapped bucket all-reduce (main_task_retrieval.py:197) leaves this to cuBLAS. */
+int univl_set_reserved_sms(int n);
 
 /* ---- GEMM (tcgen05 / TMEM / TMA) -------------------------------------------------------------------------
  * D[M,N] = epilogue(sum_k A(m,k) B(n,k)), bf16 operands, fp32 accumulation.
@@ -164,6 +169,11 @@ int univl_bert_adam_step(float* p, const float* g, float* m, float* v, void* p_b
                          int n_tensors, float* scratch, long long* step, float b1, float b2, float eps,
                          float max_grad_norm, float global_clip_norm, float warmup, long long t_total,
                          float grad_scale, void* stream);
+/* the same step reading the gradients from a bf16 buffer (the summed all-reduce payload; same element offsets as p) */
+int univl_bert_adam_step_bf16grad(float* p, const void* g_bf16, float* m, float* v, void* p_bf16, const void* segs,
+                                  int n_chunks, int n_tensors, float* scratch, long long* step, float b1, float b2,
+                                  float eps, float max_grad_norm, float global_clip_norm, float warmup,
+                                  long long t_total, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,3 +130,39 @@ def test_param_group_lr_edit_is_honoured():
     opt.step()
     d2 = float((before - p.detach()).mean())
     assert d1 > 0 and 0.05 * d1 < d2 < 0.2 * d1, (d1, d2)   # 10x smaller lr -> ~10x smaller step (m/sqrt(v) drifts a bit)
+
+
+def test_bf16_gradient_payload_equals_fp32_of_the_same_values():
+    """the data-parallel loop hands the optimizer the summed bf16 all-reduce payload (univl_bert_adam_step_bf16grad):
+    bit-identical to the fp32 path fed the same (bf16-representable) gradient values, clips included."""
+    from univl_b200.optim import FusedBertAdam
+    torch.manual_seed(0)
+    shapes = [(300, 64), (77,), (1000, 3), (5,)]
+    outs = []
+    for use_payload in (False, True):
+        torch.manual_seed(1)
+        ps = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+        opt = FusedBertAdam([{"params": ps[:2], "weight_decay": 0.01}, {"params": ps[2:], "weight_decay": 0.0}],
+                            lr=1e-3, warmup=0.1, t_total=100, max_grad_norm=1.0, global_clip_norm=1.0, grad_scale=0.5)
+        for t in range(3):
+            gen = torch.Generator(device=DEV).manual_seed(10 + t)
+            for i, p in enumerate(ps):
+                g = torch.randn(p.shape, device=DEV, generator=gen).to(torch.bfloat16).float()
+                p.grad = None if (i == 3 and t == 1) else g      # a tensor without gradient is skipped (sumsq == 0)
+            if use_payload:
+                if not opt._built:
+                    opt._build()
+                opt.g.zero_()                                      # (padding still holds the NaNs of the last round)
+                opt._gather_grads()
+                payload = opt.g.to(torch.bfloat16)
+                assert torch.equal(payload.float(), opt.g)
+                opt.g.fill_(float("nan"))                          # must not be read
+                opt.grad_payload = payload
+            opt.step()
+            opt.grad_payload = None
+        outs.append([p.detach().clone() for p in ps])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        opt.grad_payload = torch.zeros(3, device=DEV, dtype=torch.bfloat16)
+        opt.step()

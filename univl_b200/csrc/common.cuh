@@ -20,6 +20,8 @@ typedef __nv_bfloat16 bf16;
 // error plumbing shared by all translation units (defined in api.cu)
 // ----------------------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);
+int usable_sms();        // SM count minus univl_set_reserved_sms (api.cu)
+int usable_sm_pairs();  // TPCs with both SMs free under the same reservation
 #define UNIVL_OK 0
 #define UNIVL_ERR_ARG -1
 #define UNIVL_ERR_CUDA -2

@@ -643,9 +643,7 @@ extern "C" int univl_fused_qkv_attention_fwd(const void* x, long long ldx, const
   // that the rows a partial box spills into the next block are that block's true values
   p.x_box_rows = (p.RB % 32 == 0) ? p.RB : 128;
   if ((rc = make_tmap(&tx, x, p.T, H, ldx, p.x_box_rows))) return rc;   // box {64 k, x_box_rows}
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = usable_sms();
   // tuning: UNIVL_FA_MULTICAST=1 enables the 2-CTA weight multicast.  Measured (1024 x 96): L2 slice reads -30% but the
   // same 6.2 GB cross the crossbar into the SMs and the kernel is 5% slower: the bound is per-SM ingress, not L2 slices.
   static int mc_mode = -1;
@@ -1084,9 +1082,7 @@ extern "C" int univl_fused_attention_bwd(const void* qkv, long long ld_qkv, cons
   cudaError_t e = cudaFuncSetAttribute(fused_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        FB_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "fused_attention_bwd smem attribute: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = usable_sms();
   const long long items = (long long)p.n_blocks * heads;
   const int grid = (int)(items < sms ? items : sms);
   e = launch_kernel(fused_attention_bwd_kernel, dim3(grid), dim3(FB_THREADS), (size_t)FB_SMEM_BYTES,

@@ -300,9 +300,7 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
   auto kern = gemm_tcgen05_persistent_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = usable_sms();
   const long long work =
       (long long)((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
@@ -329,13 +327,11 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   auto kern = gemm_tcgen05_2cta_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int max_pairs = usable_sm_pairs();
   const long long work =
       (long long)((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (long long)splits;
   if (work > 0x7fffffffLL) return set_error(UNIVL_ERR_ARG, "gemm: too many tiles");
-  const int pairs = (int)(work < sms / 2 ? work : sms / 2);
+  const int pairs = (int)(work < max_pairs ? work : max_pairs);
   e = launch_kernel(kern, dim3(2 * pairs), dim3(GEMM_P_THREADS), (size_t)L::DYN_BYTES, stream, ta, tb, to, tx, p, (int)work);
   if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   UNIVL_CHECK_LAUNCH("gemm_tcgen05_2cta");

@@ -32,19 +32,35 @@ struct AdamCfg {
   float grad_scale;        // e.g. 1 / world_size after a sum all-reduce
 };
 
+// gradients arrive as fp32 (the buffer backward accumulates into) or as the bf16 all-reduce payload (univl_b200/ddp.py),
+// which the optimizer then reads directly instead of through an expanded fp32 copy
+__device__ __forceinline__ float4 load_grad4(const float* g, long long e) {
+  return *reinterpret_cast<const float4*>(g + e);
+}
+__device__ __forceinline__ float4 load_grad4(const bf16* g, long long e) {
+  const uint2 u = *reinterpret_cast<const uint2*>(g + e);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float load_grad(const float* g, long long e) { return g[e]; }
+__device__ __forceinline__ float load_grad(const bf16* g, long long e) { return __bfloat162float(g[e]); }
+
+template <typename G>
 __global__ void __launch_bounds__(256)
-adam_sumsq_kernel(const float* __restrict__ g, const AdamSeg* __restrict__ segs, float* __restrict__ sumsq,
+adam_sumsq_kernel(const G* __restrict__ g, const AdamSeg* __restrict__ segs, float* __restrict__ sumsq,
                   float grad_scale) {
   __shared__ float red[8];
   const AdamSeg s = segs[blockIdx.x];
-  const float* gp = g + s.offset;
   float acc = 0.f;
   for (int i = threadIdx.x * 4; i < s.count; i += blockDim.x * 4) {
     if (i + 4 <= s.count) {
-      const float4 x = *reinterpret_cast<const float4*>(gp + i);
+      const float4 x = load_grad4(g, s.offset + i);
       acc += (x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * grad_scale * grad_scale;
     } else {
-      for (int j = i; j < s.count; ++j) acc += gp[j] * gp[j] * grad_scale * grad_scale;
+      for (int j = i; j < s.count; ++j) {
+        const float x = load_grad(g, s.offset + j);
+        acc += x * x * grad_scale * grad_scale;
+      }
     }
   }
   acc = warp_sum(acc);
@@ -72,8 +88,9 @@ __global__ void adam_total_kernel(float* __restrict__ sumsq, int n_tensors) {
   }
 }
 
+template <typename G>
 __global__ void __launch_bounds__(256)
-adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adam_update_kernel(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                    bf16* __restrict__ p_bf16, const AdamSeg* __restrict__ segs, const float* __restrict__ sumsq,
                    int n_tensors, const long long* __restrict__ step, AdamCfg cfg) {
   const AdamSeg s = segs[blockIdx.x];
@@ -95,7 +112,7 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
   for (int i = threadIdx.x * 4; i < s.count; i += blockDim.x * 4) {
     const long long e = s.offset + i;
     if (i + 4 <= s.count) {
-      const float4 g4 = *reinterpret_cast<const float4*>(g + e);
+      const float4 g4 = load_grad4(g, e);
       float4 m4 = *reinterpret_cast<const float4*>(m + e);
       float4 v4 = *reinterpret_cast<const float4*>(v + e);
       float4 p4 = *reinterpret_cast<const float4*>(p + e);
@@ -119,7 +136,7 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     } else {
       for (int j = i; j < s.count; ++j) {
         const long long ee = s.offset + j;
-        const float gr = g[ee] * gmul;
+        const float gr = load_grad(g, ee) * gmul;
         const float mm = cfg.b1 * m[ee] + (1.f - cfg.b1) * gr;
         const float vv = cfg.b2 * v[ee] + (1.f - cfg.b2) * gr * gr;
         float pp = p[ee];
@@ -140,21 +157,39 @@ using namespace univl;
 // One optimizer step over flat buffers.  segs: device array of n_chunks {int64 offset, int32 count, int32 tensor,
 // float lr, float weight_decay, -, -} — one CTA per chunk (chunks of <= 64K elements, offsets multiples of 64);
 // scratch: n_tensors + 1 floats; step: device int64 (incremented).  p_bf16 (same element offsets as p) may be null.
+template <typename G>
+static int adam_step(float* p, const G* g, float* m, float* v, void* p_bf16, const void* segs, int n_chunks,
+                     int n_tensors, float* scratch, long long* step, const AdamCfg& cfg, void* stream) {
+  UNIVL_CHECK_ARG(p && g && m && v && segs && scratch && step, "bert_adam_step: null pointer");
+  UNIVL_CHECK_ARG(n_tensors > 0 && n_chunks >= n_tensors, "bert_adam_step: bad tensor / chunk count");
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdamSeg* s = reinterpret_cast<const AdamSeg*>(segs);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)(n_tensors + 1) * sizeof(float), st);
+  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "bert_adam_step memset: %s", cudaGetErrorString(e));
+  adam_sumsq_kernel<G><<<n_chunks, 256, 0, st>>>(g, s, scratch, cfg.grad_scale);
+  adam_total_kernel<<<1, 256, 0, st>>>(scratch, n_tensors);
+  adam_update_kernel<G><<<n_chunks, 256, 0, st>>>(p, g, m, v, (bf16*)p_bf16, s, scratch, n_tensors, step, cfg);
+  adam_step_inc_kernel<<<1, 1, 0, st>>>(step);
+  UNIVL_CHECK_LAUNCH("bert_adam_step");
+  return UNIVL_OK;
+}
+
 extern "C" int univl_bert_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, const void* segs,
                                     int n_chunks, int n_tensors, float* scratch, long long* step, float b1, float b2,
                                     float eps, float max_grad_norm, float global_clip_norm, float warmup,
                                     long long t_total, float grad_scale, void* stream) {
-  UNIVL_CHECK_ARG(p && g && m && v && segs && scratch && step, "bert_adam_step: null pointer");
-  UNIVL_CHECK_ARG(n_tensors > 0 && n_chunks >= n_tensors, "bert_adam_step: bad tensor / chunk count");
-  cudaStream_t st = (cudaStream_t)stream;
   AdamCfg cfg{b1, b2, eps, max_grad_norm, global_clip_norm, warmup, t_total, grad_scale};
-  const AdamSeg* s = reinterpret_cast<const AdamSeg*>(segs);
-  cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)(n_tensors + 1) * sizeof(float), st);
-  if (e != cudaSuccess) return set_error(UNIVL_ERR_CUDA, "bert_adam_step memset: %s", cudaGetErrorString(e));
-  adam_sumsq_kernel<<<n_chunks, 256, 0, st>>>(g, s, scratch, grad_scale);
-  adam_total_kernel<<<1, 256, 0, st>>>(scratch, n_tensors);
-  adam_update_kernel<<<n_chunks, 256, 0, st>>>(p, g, m, v, (bf16*)p_bf16, s, scratch, n_tensors, step, cfg);
-  adam_step_inc_kernel<<<1, 1, 0, st>>>(step);
-  UNIVL_CHECK_LAUNCH("bert_adam_step");
-  return UNIVL_OK;
+  return adam_step<float>(p, g, m, v, p_bf16, segs, n_chunks, n_tensors, scratch, step, cfg, stream);
+}
+
+// Same step with the gradients read from a bf16 buffer (same element offsets as p): the summed all-reduce payload of
+// univl_b200.ddp.FlatGradReducer(compress="bf16"), consumed without expanding it to fp32 first.
+extern "C" int univl_bert_adam_step_bf16grad(float* p, const void* g_bf16, float* m, float* v, void* p_bf16,
+                                             const void* segs, int n_chunks, int n_tensors, float* scratch,
+                                             long long* step, float b1, float b2, float eps, float max_grad_norm,
+                                             float global_clip_norm, float warmup, long long t_total,
+                                             float grad_scale, void* stream) {
+  AdamCfg cfg{b1, b2, eps, max_grad_norm, global_clip_norm, warmup, t_total, grad_scale};
+  return adam_step<bf16>(p, reinterpret_cast<const bf16*>(g_bf16), m, v, p_bf16, segs, n_chunks, n_tensors, scratch,
+                         step, cfg, stream);
 }

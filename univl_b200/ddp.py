@@ -88,61 +88,81 @@ class FlatGradReducer:
 
 
 class PhasedBackward:
-    """Backward in two phases so the gradient exchange of phase 1 overlaps the compute of phase 2.
+    """Backward in phases so the gradient exchange of one phase overlaps the compute of the next.
 
     The reference's DDP overlaps bucketed all-reduces with the rest of backward through autograd hooks
     (main_task_retrieval.py:197-198).  Here the step is replayed from CUDA graphs, which cannot contain the NCCL calls,
-    so the backward is cut at one tensor instead: the hidden state entering text-encoder layer `split_layer`.
-      phase 1  loss -> cross encoder -> visual encoder (side stream) and text layers 11 .. split_layer
-               => every gradient of the cross / visual / similarity parameters and of the upper text layers is final
-      phase 2  text layers split_layer-1 .. 0 and the text embeddings
-    `phase1_ranges` / `phase2_ranges` are the contiguous runs of the flat gradient buffer each phase completes, so the
-    caller can all-reduce the first set while phase 2 runs (bench.py).  Needs the flat layout (`FusedBertAdam(model=)`).
+    so the autograd graph is cut instead, at the hidden states entering the text-encoder layers `cut_layers`
+    (descending, e.g. (9, 5)): the forward continues from a detached leaf there (modules/transformer.py EncoderStack.run).
+      phase 0   loss.backward(): heads, cross encoder, decoder, visual encoder (side stream), text layers 11 .. c0
+      phase i   text layers c(i-1)-1 .. c(i)          (seeded with the gradient phase i-1 left on its cut leaf)
+      last      text layers c(last)-1 .. 0 and the text embeddings (the word table is tied to the decoder / MLM heads,
+                so its gradient is only complete here)
+    `ranges[i]` are the contiguous runs of the flat gradient buffer that are final once phase i has run; the caller
+    all-reduces them while phase i+1 computes (bench.py).  Parameters outside the 2-D weight arena (biases, LayerNorm
+    vectors, 0.2 % of the bytes) go with the last phase.  Needs the flat layout (`FusedBertAdam(..., model=model)`).
     """
 
-    def __init__(self, model, flat, split_layer):
+    def __init__(self, model, flat, cut_layers):
         self.model, self.flat = model, flat
-        self.split_layer = int(split_layer)
+        cuts = sorted({int(c) for c in cut_layers}, reverse=True)
         stack = model.bert.encoder
-        if not 0 < self.split_layer < len(stack.layer):
-            raise ValueError("PhasedBackward: split_layer must be inside the text stack")
-        stack.__dict__["_split_at"] = self.split_layer
-        late = set()
+        if not cuts or not all(0 < c < len(stack.layer) for c in cuts):
+            raise ValueError("PhasedBackward: cut layers must lie inside the text stack, got %r" % (cut_layers,))
+        self.cuts = cuts
+        self.n_phases = len(cuts) + 1
+        stack.__dict__["_cut_layers"] = frozenset(cuts)
+        arena_end = flat.arena.buf.numel() if flat.arena.entries else 0
+        last = self.n_phases - 1
+        label = {}
         for name, p in model.named_parameters():
+            ph = 0
             if name.startswith("bert.embeddings."):
-                late.add(id(p))
+                ph = last
             elif name.startswith("bert.encoder.layer."):
-                if int(name.split(".")[3]) < self.split_layer:
-                    late.add(id(p))
-        # tied tables (decoder / MLM heads share the word table) receive gradients in phase 1 too: they complete in phase 2
-        self.phase2_ranges = self._runs([p for p in flat.params if id(p) in late])
-        self.phase1_ranges = self._runs([p for p in flat.params if id(p) not in late])
-        # leaves at the far end of each phase's sub-graph: asking autograd for their gradients makes it run the whole
-        # branch (the kernels accumulate into the flat buffer themselves and hand autograd None)
-        self._far1 = [model.visual.embeddings.position_embeddings.weight, model.normalize_video.visual_norm2d.weight]
-        self._far2 = [model.bert.embeddings.word_embeddings.weight]
-        self._g_split = None
-
-    def _runs(self, params):
-        segs = sorted((self.flat.by_id[id(p)][0], self.flat.by_id[id(p)][1]) for p in params)
-        runs = []
-        for off, n in segs:
-            end = off + (n + 63) // 64 * 64
-            if runs and off <= runs[-1][1]:
-                runs[-1][1] = max(runs[-1][1], end)
+                li = int(name.split(".")[3])
+                ph = sum(1 for c in cuts if li < c)
+            if flat.by_id[id(p)][0] >= arena_end:
+                ph = last
+            label[id(p)] = max(ph, label.get(id(p), 0))          # tied parameters: the latest phase that touches them
+        segs = sorted((flat.by_id[id(p)][0], flat.by_id[id(p)][1], label[id(p)]) for p in flat.params)
+        self.ranges = [[] for _ in range(self.n_phases)]
+        prev = None
+        for off, n, ph in segs:
+            if ph == prev:                      # neighbour in the buffer, same phase: extend the run (gap included)
+                self.ranges[ph][-1][1] = off + n
             else:
-                runs.append([off, end])
-        total = self.flat.total
-        return [(a, min(b, total)) for a, b in runs]
+                self.ranges[ph].append([off, off + n])
+            prev = ph
+        # pad each run to its 64-element slot (the padding holds zeros; keeps bf16 payload slices 128-byte aligned)
+        self.ranges = [[(a, min((b + 63) // 64 * 64, flat.total)) for a, b in runs] for runs in self.ranges]
+        self._pairs = None
 
-    def phase1(self, loss):
-        split = self.model.bert.encoder.__dict__.get("_split_tensor")
-        if split is None:
-            raise RuntimeError("PhasedBackward: the text encoder did not run in this forward")
-        grads = torch.autograd.grad(loss, [split] + self._far1, allow_unused=True)
-        self._split, self._g_split = split, grads[0]
+    def covered(self):
+        """total elements in all ranges (== flat.total when every slot is covered; asserted by the tests)"""
+        return sum(b - a for runs in self.ranges for a, b in runs)
 
-    def phase2(self):
-        torch.autograd.grad([self._split], self._far2, grad_outputs=[self._g_split], allow_unused=True)
-        self._split = self._g_split = None
-        self.model.bert.encoder.__dict__.pop("_split_tensor", None)
+    def _stack(self):
+        return self.model.bert.encoder.__dict__
+
+    def begin(self):
+        """call before the forward of every step (drops the cut tensors of the previous one)"""
+        self._stack().pop("_cut_pairs", None)
+
+    def backward(self, phase, loss=None):
+        """run phase `phase` (0 takes the loss)"""
+        if phase == 0:
+            pairs = self._stack().pop("_cut_pairs", None)
+            if not pairs:
+                raise RuntimeError("PhasedBackward: the text encoder did not run (or ran without grad) in this forward")
+            self._pairs = pairs
+            loss.backward()
+            return
+        cut = self.cuts[phase - 1]
+        outs = [x for i, x, leaf in self._pairs if i == cut]
+        grads = [leaf.grad for i, x, leaf in self._pairs if i == cut]
+        if any(g is None for g in grads):
+            raise RuntimeError("PhasedBackward: no gradient reached the cut at text layer %d" % cut)
+        torch.autograd.backward(outs, grads)
+        if phase == self.n_phases - 1:
+            self._pairs = None

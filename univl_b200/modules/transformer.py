@@ -116,10 +116,12 @@ class EncoderStack(nn.Module):
 
     def run(self, x2d, n_seq, S, mask, keep_all=False):
         outs = []
-        split_at = self.__dict__.get("_split_at")   # univl_b200.ddp.PhasedBackward: remember the input of this layer
+        cuts = self.__dict__.get("_cut_layers")   # univl_b200.ddp.PhasedBackward: cut the autograd graph at these layers
         for i, layer in enumerate(self.layer):
-            if split_at is not None and i == split_at and x2d.requires_grad:
-                self.__dict__["_split_tensor"] = x2d
+            if cuts and i in cuts and x2d.requires_grad:
+                leaf = x2d.detach().requires_grad_(True)
+                self.__dict__.setdefault("_cut_pairs", []).append((i, x2d, leaf))
+                x2d = leaf
             x2d = layer.run(x2d, n_seq, S, mask)
             if keep_all:
                 outs.append(x2d)

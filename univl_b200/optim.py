@@ -130,6 +130,9 @@ class FusedBertAdam(torch.optim.Optimizer):
         super(FusedBertAdam, self).__init__(params, defaults)
         self.global_clip_norm = float(global_clip_norm)
         self.grad_scale = float(grad_scale)
+        # bf16 gradients to read INSTEAD of the fp32 buffer (the summed payload of ddp.FlatGradReducer(compress="bf16"));
+        # set by the data-parallel loop, None = read self.g
+        self.grad_payload = None
         self.model = model
         self.sink_grads = sink_grads
         self._built = False
@@ -280,7 +283,12 @@ class FusedBertAdam(torch.optim.Optimizer):
         if self._group_signature() != self._sig:
             self._build_segs()
         g0 = self.param_groups[0]
-        call("univl_bert_adam_step", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+        payload = self.grad_payload
+        if payload is not None and (payload.dtype != torch.bfloat16 or payload.numel() != self.g.numel()
+                                    or payload.device != self.g.device):
+            raise ValueError("FusedBertAdam.grad_payload must be a bf16 tensor shaped like the flat gradient buffer")
+        call("univl_bert_adam_step" if payload is None else "univl_bert_adam_step_bf16grad", self.p.data_ptr(),
+             (self.g if payload is None else payload).data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
              None if self.shadow is None else self.shadow.data_ptr(), self.segs.data_ptr(), self.n_chunks,
              self.n_tensors, self.scratch.data_ptr(), self.step_dev.data_ptr(), float(g0["b1"]), float(g0["b2"]),
              float(g0["e"]), float(g0["max_grad_norm"]), self.global_clip_norm, float(g0["warmup"]),

@@ -39,6 +39,12 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def reserve_sms(n):
+    """SMs a concurrent collective occupies while the kernels enqueued from now on run (include/univl_b200.h
+    univl_set_reserved_sms): persistent grids shrink to the free SMs.  Captured graphs keep the grids they were built with."""
+    lib.call("univl_set_reserved_sms", int(n))
+
+
 class WeightArena:
     """bf16 shadow copies of every >=2-D parameter of a module tree, in one flat buffer."""
 
