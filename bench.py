@@ -27,7 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-AUTO_CUTS = "off"   # measured: no gain at N=2 (the all-reduce under the backward slows it by what it hides), see DESIGN.md
+# Measured (profiles/r02_overlap_sweep.md): cutting the backward at text layer 6 and all-reducing the finished 61 % of the
+# gradient bytes under the remaining backward gains 3.5 % at N=8 (NVLS all-reduce); at N=2 (ring all-reduce, SM copies)
+# the collective slows the backward by what it hides, so the cut is only taken for world > 2.
+AUTO_CUTS = "6"
 
 
 def parse():
@@ -51,7 +54,7 @@ def parse():
                     help="N > 1: dtype of the gradient all-reduce payload (bf16 halves the NVLink bytes)")
     ap.add_argument("--overlap_cuts", default="auto", help="N > 1: text-encoder layers at which the backward is cut into "
                     "phases whose gradient all-reduce overlaps the next phase (univl_b200.ddp.PhasedBackward), e.g. "
-                    "'9,5'; '' or 'off' = one all-reduce after the whole backward; auto = " + AUTO_CUTS)
+                    "'9,5'; '' or 'off' = one all-reduce after the whole backward; auto = '6' for more than 2 GPUs, else off")
     ap.add_argument("--overlap_sms", type=int, default=0, help="SMs left to the overlapped all-reduce: NCCL_MAX_CTAS and "
                     "the reservation the persistent kernels of the overlapped phases size their grids for")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (falls back to eager "
@@ -274,7 +277,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    cuts = AUTO_CUTS if a.overlap_cuts == "auto" else a.overlap_cuts
+    cuts = a.overlap_cuts
+    if cuts == "auto":
+        cuts = AUTO_CUTS if world > 2 else "off"
     overlap = world > 1 and a.graph and cuts not in ("", "off", "0")
     if world > 1:
         if overlap and a.overlap_sms > 0:

@@ -54,4 +54,4 @@ def test_phases_reproduce_single_backward(mode, cuts):
     assert l0 == l1
     assert float(g0.norm()) > 0
     # same kernels on the same inputs; only the order of fp32 atomic accumulations may differ
-    torch.testing.assert_close(g1, g0, rtol=1e-4, atol=1e-6 * float(g0.abs().max()))
+    torch.testing.assert_close(g1, g0, rtol=1e-4, atol=1e-5 * float(g0.abs().max()))
