@@ -42,6 +42,39 @@ def test_gemm_all_operand_majors(a_mn, b_mn, shape):
     assert (acc - (ref - bias + 1.0)).abs().max() <= 2e-3 * ref.abs().max()
 
 
+def test_reserved_sms_shrink_persistent_grids_not_results():
+    """univl_set_reserved_sms: persistent kernels launched while a collective holds SMs use fewer CTAs (each walks more
+    tiles); every output is unchanged — GEMM (1-CTA and CTA-pair tiles) and the fused attention forward / backward."""
+    g = torch.Generator(device=DEV).manual_seed(4)
+    cases = [(1536, 768, 768), (2560, 3072, 768), (300, 200, 136)]
+    mats = [(_bf(torch.randn(M, K, device=DEV, generator=g) * 0.5), _bf(torch.randn(N, K, device=DEV, generator=g) * 0.5))
+            for M, N, K in cases]
+    x, w, b, mask = _fused_inputs(40, 96, 11)
+    spec = ops.MaskSpec(mask, causal=False)
+
+    def run():
+        outs = []
+        for (M, N, K), (A, B) in zip(cases, mats):
+            out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            outs.append(ops.gemm(A, B, M, N, K, out, epi=ops.EPI_BIAS))
+        o, lse, qkv = ops.fused_qkv_attention_fwd(x, w, b, 40, 96, spec)
+        dqkv = torch.empty_like(qkv)
+        ops.fused_attention_bwd(qkv, o, lse, o, dqkv, 40, 96, spec, p=0.0, seed=RNG.data_ptr(), stream=7)
+        torch.cuda.synchronize()
+        return outs + [o, lse, dqkv]
+    base = run()
+    try:
+        for n in (16, 40):
+            rt.reserve_sms(n)
+            for a, c in zip(base, run()):
+                assert torch.equal(a, c), n
+    finally:
+        rt.reserve_sms(0)
+    with pytest.raises(RuntimeError):
+        rt.reserve_sms(-1)
+
+
+# ---------------------------------------------------------------------------------------------------------
 def test_gemm_fused_epilogues():
     M, N, K = 384, 3072, 768
     g = torch.Generator(device=DEV).manual_seed(2)
