@@ -51,7 +51,8 @@ def test_phases_reproduce_single_backward(mode, cuts):
 
     l0, g0 = flat_grads(None)
     l1, g1 = flat_grads(cuts)
-    assert l0 == l1
+    # (the cross-entropy losses sum their rows with fp32 atomics: the last bits depend on the arrival order)
+    assert abs(l0 - l1) <= 1e-6 * max(1.0, abs(l0)), (l0, l1)
     assert float(g0.norm()) > 0
     # same kernels on the same inputs; only the order of fp32 atomic accumulations may differ
     torch.testing.assert_close(g1, g0, rtol=1e-4, atol=1e-5 * float(g0.abs().max()))
