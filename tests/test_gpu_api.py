@@ -151,3 +151,30 @@ def test_cuda_graph_replay_draws_fresh_dropout_masks():
         graph.replay()
         vals.append(float(loss))
     assert len(set(vals)) == 4, vals  # same launch arguments, different device-side RNG epoch each replay
+
+
+def test_device_side_masking_feeds_pretrain_stage_two():
+    """univl_b200.masking samples the MLM / MFM masks on the device (dataloader_howto100m.py:103-125, :314-329 restated):
+    the model accepts the result in place of the dataloader's four tensors, and with the SAME masks moved to the CPU the
+    oracle agrees on the loss."""
+    from univl_b200 import masking
+    from tests.oracle_util import run_oracle
+    cfg = synth.task_config(mode="pretrain2", batch_size=4, max_words=16, max_frames=12, text_layers=2, visual_layers=1,
+                            cross_layers=1, decoder_layers=1)
+    sd = synth.make_state_dict(cfg, seed=5)
+    batch = synth.make_batch(cfg, seed=6)
+    for k in ("pairs_masked_text", "pairs_token_labels", "masked_video", "video_labels_index"):
+        batch.pop(k)
+    dev_batch = to_device(batch)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    full = masking.mask_pretrain_batch(dev_batch, p=0.3, generator=gen)   # p raised so the tiny batch surely has picks
+    assert all(v.is_cuda for v in full.values())
+    assert int((full["pairs_token_labels"] != -1).sum()) > 0 and int((full["video_labels_index"] != -1).sum()) > 0
+    model = build_model(cfg, sd=sd)
+    loss = model(**full)
+    loss.backward()
+    got = float(loss.detach())
+    o_loss, parts, _ = run_oracle(cfg, {k: v.cpu() for k, v in full.items()}, sd=sd, backward=False)
+    # pretrain stage-two tolerance of test_gpu_model_parity.py, with 65 bounding the joint-similarity logits of these weights
+    tol = 2e-3 * abs(float(o_loss)) + 2.0 ** -7 * (65.0 + float(parts["mfm_loss"]))
+    assert abs(got - float(o_loss)) <= tol, (got, float(o_loss), tol)
