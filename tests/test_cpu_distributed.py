@@ -130,6 +130,9 @@ def test_phased_backward_ranges_tile_the_buffer():
     assert phase_of(enc[0].w.weight) == 2
     assert phase_of(model.bert.embeddings.word_embeddings.weight) == 2      # tied table: complete only at the end
     assert phase_of(enc[3].w.bias) == 2 and phase_of(model.visual[1].w.bias) == 2   # vectors ride with the last phase
+    assert model.bert.encoder.__dict__["_cut_layers"] == frozenset((3, 1))
+    ph.remove()
+    assert "_cut_layers" not in model.bert.encoder.__dict__
     with pytest.raises(ValueError):
         _mock_phased((0,))
     with pytest.raises(ValueError):

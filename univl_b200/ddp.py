@@ -149,6 +149,12 @@ class PhasedBackward:
         """call before the forward of every step (drops the cut tensors of the previous one)"""
         self._stack().pop("_cut_pairs", None)
 
+    def remove(self):
+        """take the cuts out of the text stack again: later forwards build one autograd graph, as before"""
+        self._stack().pop("_cut_layers", None)
+        self._stack().pop("_cut_pairs", None)
+        self._pairs = None
+
     def backward(self, phase, loss=None):
         """run phase `phase` (0 takes the loss)"""
         if phase == 0:
