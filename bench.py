@@ -14,6 +14,10 @@ One JSON line on stdout (rank 0).  `value` = whole-job samples/s with inputs res
 driven from pinned HOST buffers (H2D of every input and D2H of the loss inside the timed region); `roofline` = the
 tcgen05 GEMM kernel's achieved TFLOP/s (CUDA events around its launches) against the measured bf16 peak;
 `cpu_baseline` = the CPU oracle (port of the reference algorithm) timed on this box's host cores on a bounded sample.
+
+N > 1: the gradients travel as a bf16 payload that the optimizer reads directly; for more than 2 GPUs the backward is cut at
+text layer 6 (`--overlap_cuts`) so the all-reduce of the finished 61 % of the bytes runs under the rest of the backward
+(univl_b200.ddp.PhasedBackward); `step_breakdown_ms` = rank 0's device time per segment of such a step.
 """
 import argparse
 import json
